@@ -1,0 +1,561 @@
+// libdspgn.so host side: handles, weight packing, batch upload, launch sequencing.  C ABI in
+// include/dspgn.h.  No torch, no exceptions across the boundary.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "dspgn_common.cuh"
+#include "dspgn_simt.cuh"
+#include "dspgn_solve.cuh"
+#include "dspgn_tc.cuh"
+
+using namespace dspgn;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(DSPGN_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return -1; }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf {   // pinned staging
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); return -1; }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct DspgnDecoder {
+  int device = 0;
+  DspgnDecoderSpec spec{};
+  DecoderDev dev{};
+  std::vector<void*> allocs;
+  TcDecoderHost tc;
+};
+
+struct DspgnSolver {
+  int device = 0;
+  int num_sms = 0;
+  int engine = DSPGN_ENGINE_SIMT;
+  DspgnConfig cfg{};
+  cudaStream_t stream = nullptr;
+  std::vector<DspgnDecoder*> classes;
+  DevBuf d_decs;
+  // resident batch
+  int n_obj = 0;
+  int tot_pts = 0, tot_rays = 0, tot_fg = 0;
+  long long tot_smp = 0;
+  int max_rays = 0;
+  std::vector<ObjMeta> h_meta;
+  HostBuf h_stage;
+  DevBuf d_stage;        // one contiguous upload: meta | T_init | code_init | pts | rays | depth
+  ObjMeta* d_meta = nullptr; float* d_Tinit = nullptr; float* d_code = nullptr;
+  float* d_pts = nullptr; float* d_rays = nullptr; float* d_depth = nullptr;
+  DevBuf d_state, d_acc, d_V, d_m, d_results, d_active;
+  DevBuf d_sdf, d_bx, d_bs, d_br;
+  DevBuf d_dbg;
+  HostBuf h_results;
+  // counters
+  DspgnCounters ctr{};
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;
+};
+
+namespace {
+
+int check_spec(const DspgnDecoderSpec& s) {
+  if (s.num_linear < 3 || s.num_linear > 9) return fail(DSPGN_E_ARG, "num_linear must be in [3,9]");
+  if (s.latent_size < 1 || s.latent_size > DSPGN_MAX_CODE) return fail(DSPGN_E_ARG, "latent_size must be <= 64");
+  const int in0 = s.latent_size + 3;
+  if (s.in_dim[0] != in0) return fail(DSPGN_E_ARG, "in_dim[0] must equal latent_size+3");
+  if (s.out_dim[s.num_linear - 1] != 1) return fail(DSPGN_E_ARG, "last layer must have one output");
+  for (int k = 0; k < s.num_linear; ++k) {
+    if (s.in_dim[k] < 1 || s.in_dim[k] > kHid || s.out_dim[k] < 1 || s.out_dim[k] > kHid)
+      return fail(DSPGN_E_ARG, "layer widths must be in [1,256]");
+    if (k > 0) {
+      const int expect = s.out_dim[k - 1] + (k == s.latent_in_layer ? in0 : 0);
+      if (s.in_dim[k] != expect) return fail(DSPGN_E_ARG, "layer in_dim inconsistent with previous out_dim/latent_in");
+    }
+  }
+  if (s.latent_in_layer != -1 && (s.latent_in_layer < 1 || s.latent_in_layer > s.num_linear - 2))
+    return fail(DSPGN_E_ARG, "latent_in_layer must be a hidden layer index or -1");
+  return 0;
+}
+
+int upload_vec(DspgnDecoder* d, const std::vector<float>& h, const float** out) {
+  void* p = nullptr;
+  CU(cudaMalloc(&p, h.size() * sizeof(float)));
+  d->allocs.push_back(p);
+  CU(cudaMemcpy(p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *out = reinterpret_cast<const float*>(p);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dspgn_last_error(void) { return g_err.c_str(); }
+int dspgn_version(void) { return 100; }
+
+int dspgn_decoder_create(const DspgnDecoderSpec* spec, const float* const* W, const float* const* b,
+                         int device, DspgnDecoder** out) {
+  if (!spec || !W || !b || !out) return fail(DSPGN_E_ARG, "null argument");
+  if (int rc = check_spec(*spec)) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(DSPGN_E_NOGPU, "no CUDA device"); }
+  if (device < 0 || device >= ndev) return fail(DSPGN_E_ARG, "bad device index");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(DSPGN_E_NOGPU, "libdspgn is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+  DspgnDecoder* d = new (std::nothrow) DspgnDecoder();
+  if (!d) return fail(DSPGN_E_ALLOC, "oom");
+  d->device = device;
+  d->spec = *spec;
+  DecoderDev& dv = d->dev;
+  dv.L = spec->latent_size; dv.n_lin = spec->num_linear; dv.latent_in = spec->latent_in_layer; dv.in0 = spec->latent_size + 3;
+  const int nl = spec->num_linear;
+  int rc = 0;
+  for (int k = 0; k < nl && rc == 0; ++k) {
+    const int nin = spec->in_dim[k], nout = spec->out_dim[k];
+    dv.in_dim[k] = nin; dv.out_dim[k] = nout;
+    const int in_pad = (nin + kKC - 1) / kKC * kKC, out_pad = (nout + kKC - 1) / kKC * kKC;
+    std::vector<float> wf((size_t)in_pad * kHid, 0.f), wb((size_t)out_pad * kHid, 0.f), bb(kHid, 0.f);
+    for (int j = 0; j < nout; ++j) {
+      for (int i = 0; i < nin; ++i) {
+        const float w = W[k][(size_t)j * nin + i];
+        wf[(size_t)i * kHid + j] = w;
+        wb[(size_t)j * kHid + i] = w;
+      }
+      bb[j] = b[k][j];
+    }
+    rc = upload_vec(d, wf, &dv.Wf[k]);
+    if (!rc) rc = upload_vec(d, wb, &dv.Wb[k]);
+    if (!rc) rc = upload_vec(d, bb, &dv.bias[k]);
+    if (!rc && k == nl - 1) {
+      std::vector<float> wl(kHid, 0.f);
+      for (int i = 0; i < nin; ++i) wl[i] = W[k][i];
+      rc = upload_vec(d, wl, &dv.w_last);
+    }
+  }
+  if (!rc) rc = tc_pack_decoder(*spec, W, b, d->tc, &dv, g_err);
+  if (rc) { dspgn_decoder_destroy(d); return rc; }
+  *out = d;
+  return 0;
+}
+
+void dspgn_decoder_destroy(DspgnDecoder* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  for (void* p : d->allocs) cudaFree(p);
+  tc_free_decoder(d->tc);
+  delete d;
+}
+
+int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, int n_classes, int device,
+                        DspgnSolver** out) {
+  if (!cfg || !classes || !out) return fail(DSPGN_E_ARG, "null argument");
+  if (n_classes < 1 || n_classes > DSPGN_MAX_CLASSES) return fail(DSPGN_E_ARG, "n_classes must be in [1,4]");
+  if (cfg->num_depth_samples < 2 || cfg->num_depth_samples > 64) return fail(DSPGN_E_ARG, "num_depth_samples must be in [2,64]");
+  if (cfg->pose_only_iterations > 5) return fail(DSPGN_E_ARG, "pose_only_iterations > 5 (inlier cut, optimizer.py:76-78) not supported");
+  if (cfg->num_iterations < 1) return fail(DSPGN_E_ARG, "num_iterations must be >= 1");
+  for (int c = 0; c < n_classes; ++c) {
+    if (!classes[c] || classes[c]->device != device) return fail(DSPGN_E_ARG, "decoder/device mismatch");
+    if (cfg->code_len < 1 || cfg->code_len > classes[c]->spec.latent_size) return fail(DSPGN_E_ARG, "code_len exceeds decoder latent_size");
+    if (cfg->code_len != classes[c]->spec.latent_size) return fail(DSPGN_E_ARG, "code_len must equal the decoder latent_size");
+  }
+  CU(cudaSetDevice(device));
+  DspgnSolver* s = new (std::nothrow) DspgnSolver();
+  if (!s) return fail(DSPGN_E_ALLOC, "oom");
+  s->device = device;
+  s->cfg = *cfg;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  s->num_sms = prop.multiProcessorCount;
+  for (int c = 0; c < n_classes; ++c) s->classes.push_back(classes[c]);
+  std::vector<DecoderDev> decs;
+  for (auto* d : s->classes) decs.push_back(d->dev);
+  if (s->d_decs.reserve(decs.size() * sizeof(DecoderDev))) { delete s; return fail(DSPGN_E_ALLOC, "cudaMalloc"); }
+  CU(cudaMemcpy(s->d_decs.p, decs.data(), decs.size() * sizeof(DecoderDev), cudaMemcpyHostToDevice));
+  bool tc_ok = true;
+  for (auto* d : s->classes) tc_ok = tc_ok && d->tc.ok;
+  int eng = cfg->engine;
+  if (eng == DSPGN_ENGINE_AUTO) {
+    const char* e = getenv("DSPGN_ENGINE");
+    if (e && !strcmp(e, "simt")) eng = DSPGN_ENGINE_SIMT;
+    else if (e && !strcmp(e, "tc")) eng = DSPGN_ENGINE_TC;
+    else eng = (tc_ok && tc_engine_default()) ? DSPGN_ENGINE_TC : DSPGN_ENGINE_SIMT;
+  }
+  if (eng == DSPGN_ENGINE_TC && !tc_ok) { delete s; return fail(DSPGN_E_ARG, "tensor-core engine unavailable for this decoder shape"); }
+  s->engine = eng;
+  CU(cudaFuncSetAttribute(k_decoder_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimtSmem)));
+  if (int rc = tc_setup_kernels(g_err)) { delete s; return rc; }
+  CU(cudaEventCreate(&s->ev_run0));
+  CU(cudaEventCreate(&s->ev_run1));
+  *out = s;
+  return 0;
+}
+
+void dspgn_solver_destroy(DspgnSolver* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaDeviceSynchronize();
+  for (DevBuf* b : {&s->d_decs, &s->d_stage, &s->d_state, &s->d_acc, &s->d_V, &s->d_m, &s->d_results, &s->d_active,
+                    &s->d_sdf, &s->d_bx, &s->d_bs, &s->d_br, &s->d_dbg}) b->release();
+  s->h_stage.release();
+  s->h_results.release();
+  for (auto e : s->ev) cudaEventDestroy(e);
+  if (s->ev_run0) cudaEventDestroy(s->ev_run0);
+  if (s->ev_run1) cudaEventDestroy(s->ev_run1);
+  delete s;
+}
+
+int dspgn_solver_set_stream(DspgnSolver* s, void* cuda_stream) {
+  if (!s) return fail(DSPGN_E_ARG, "null solver");
+  s->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  return 0;
+}
+
+int dspgn_solver_engine(const DspgnSolver* s) { return s ? s->engine : DSPGN_E_ARG; }
+
+int dspgn_enable_timing(DspgnSolver* s, int on) { if (!s) return fail(DSPGN_E_ARG, "null solver"); s->timing = on != 0; return 0; }
+
+int dspgn_counters(DspgnSolver* s, DspgnCounters* out) {
+  if (!s || !out) return fail(DSPGN_E_ARG, "null argument");
+  *out = s->ctr;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+int dspgn_upload_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in) {
+  if (!s || !in) return fail(DSPGN_E_ARG, "null argument");
+  if (n_obj < 1 || n_obj > kMaxObjScan) return fail(DSPGN_E_ARG, "n_obj must be in [1,1024]");
+  CU(cudaSetDevice(s->device));
+  const int D = s->cfg.num_depth_samples;
+  s->h_meta.assign(n_obj, ObjMeta{});
+  long long tp = 0, tr = 0, tf = 0, ts = 0;
+  int max_rays = 0;
+  for (int o = 0; o < n_obj; ++o) {
+    const DspgnObjectIn& I = in[o];
+    if (!I.t_cam_obj || I.n_pts < 1 || !I.pts) return fail(DSPGN_E_ARG, "object needs a pose and at least one surface point");
+    if (I.n_rays < 0 || I.n_depth < 0 || I.n_depth > I.n_rays) return fail(DSPGN_E_ARG, "n_depth must be <= n_rays");
+    if (I.n_rays > kScanMaxRays) return fail(DSPGN_E_ARG, "n_rays must be <= 8192");
+    if (I.class_id < 0 || I.class_id >= (int)s->classes.size()) return fail(DSPGN_E_ARG, "bad class_id");
+    ObjMeta& M = s->h_meta[o];
+    M.pts_off = (int)tp; M.n_pts = I.n_pts;
+    M.ray_off = (int)tr; M.n_rays = I.rays ? I.n_rays : 0; M.n_fg = I.rays ? I.n_depth : 0;
+    M.fg_off = (int)tf; M.smp_off = (int)ts;
+    M.class_id = I.class_id; M.scale = I.scale; M.has_code = I.code != nullptr;
+    tp += M.n_pts; tr += M.n_rays; tf += M.n_fg; ts += (long long)M.n_rays * D;
+    if (M.n_rays > max_rays) max_rays = M.n_rays;
+  }
+  if (tp > (1 << 28) || ts > (1LL << 30)) return fail(DSPGN_E_ARG, "batch too large");
+  // one staging block: meta | T_init | code | pts | rays | depth
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t o_meta = 0, o_T = al(o_meta + sizeof(ObjMeta) * n_obj), o_code = al(o_T + 64 * n_obj),
+               o_pts = al(o_code + 4 * kMaxCode * (size_t)n_obj), o_rays = al(o_pts + 12 * (size_t)tp),
+               o_depth = al(o_rays + 12 * (size_t)tr), total = al(o_depth + 4 * (size_t)tf);
+  if (s->h_stage.reserve(total) || s->d_stage.reserve(total)) return fail(DSPGN_E_ALLOC, "staging allocation failed");
+  unsigned char* hb = s->h_stage.as<unsigned char>();
+  memcpy(hb + o_meta, s->h_meta.data(), sizeof(ObjMeta) * n_obj);
+  float* hT = reinterpret_cast<float*>(hb + o_T);
+  float* hC = reinterpret_cast<float*>(hb + o_code);
+  float* hP = reinterpret_cast<float*>(hb + o_pts);
+  float* hR = reinterpret_cast<float*>(hb + o_rays);
+  float* hD = reinterpret_cast<float*>(hb + o_depth);
+  for (int o = 0; o < n_obj; ++o) {
+    const DspgnObjectIn& I = in[o];
+    const ObjMeta& M = s->h_meta[o];
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) hT[o * 16 + r * 4 + c] = I.t_cam_obj[(size_t)r * I.t_rs + (size_t)c * I.t_cs];
+    for (int i = 0; i < kMaxCode; ++i) hC[o * kMaxCode + i] = (I.code && i < s->cfg.code_len) ? I.code[i] : 0.f;
+    float* p = hP + 3 * (size_t)M.pts_off;
+    if (I.pts_cs == 1 && I.pts_rs == 3) memcpy(p, I.pts, 12 * (size_t)M.n_pts);
+    else for (int r = 0; r < M.n_pts; ++r)
+      for (int c = 0; c < 3; ++c) p[3 * (size_t)r + c] = I.pts[(size_t)r * I.pts_rs + (size_t)c * I.pts_cs];
+    float* q = hR + 3 * (size_t)M.ray_off;
+    for (int r = 0; r < M.n_rays; ++r)
+      for (int c = 0; c < 3; ++c) q[3 * (size_t)r + c] = I.rays[(size_t)r * I.rays_rs + (size_t)c * I.rays_cs];
+    if (M.n_fg) memcpy(hD + M.fg_off, I.depth, 4 * (size_t)M.n_fg);
+  }
+  CU(cudaMemcpyAsync(s->d_stage.p, hb, total, cudaMemcpyHostToDevice, s->stream));
+  unsigned char* db = s->d_stage.as<unsigned char>();
+  s->d_meta = reinterpret_cast<ObjMeta*>(db + o_meta);
+  s->d_Tinit = reinterpret_cast<float*>(db + o_T);
+  s->d_code = reinterpret_cast<float*>(db + o_code);
+  s->d_pts = reinterpret_cast<float*>(db + o_pts);
+  s->d_rays = reinterpret_cast<float*>(db + o_rays);
+  s->d_depth = reinterpret_cast<float*>(db + o_depth);
+  s->n_obj = n_obj; s->tot_pts = (int)tp; s->tot_rays = (int)tr; s->tot_fg = (int)tf; s->tot_smp = ts; s->max_rays = max_rays;
+  int bad = 0;
+  bad |= s->d_state.reserve(sizeof(ObjState) * n_obj);
+  bad |= s->d_acc.reserve(sizeof(double) * 2 * kAccStride * (size_t)n_obj);
+  bad |= s->d_V.reserve(4 * (size_t)n_obj);
+  bad |= s->d_m.reserve(4 * (size_t)n_obj);
+  bad |= s->d_results.reserve(4 * DSPGN_RESULT_FLOATS * (size_t)n_obj);
+  bad |= s->h_results.reserve(4 * DSPGN_RESULT_FLOATS * (size_t)n_obj);
+  bad |= s->d_active.reserve((size_t)tp);
+  const size_t smp = (size_t)(ts > 0 ? ts : 1);
+  if (!s->cfg.sdf_only) {
+    bad |= s->d_sdf.reserve(4 * smp);
+    bad |= s->d_bx.reserve(12 * smp);
+    bad |= s->d_bs.reserve(4 * smp);
+    bad |= s->d_br.reserve(4 * smp);
+  }
+  bad |= s->d_dbg.reserve(4 * ((size_t)kPMax * kPMax + 2 * kPMax + 8));
+  if (bad) return fail(DSPGN_E_ALLOC, "workspace allocation failed");
+  return 0;
+}
+
+namespace {
+
+cudaEvent_t next_event(DspgnSolver* s) {
+  if (s->ev_used == s->ev.size()) { cudaEvent_t e; cudaEventCreate(&e); s->ev.push_back(e); }
+  return s->ev[s->ev_used++];
+}
+
+int launch_term(DspgnSolver* s, TermArgs& a, long long rows_upper) {
+  if (s->timing) cudaEventRecord(next_event(s), s->stream);
+  const long long tile_rows = (s->engine == DSPGN_ENGINE_TC) ? kTcRows : kTP;
+  long long tiles = (rows_upper + tile_rows - 1) / tile_rows + s->n_obj;
+  if (s->engine == DSPGN_ENGINE_TC) {
+    if (int rc = tc_launch_term(a, s->num_sms, tiles, s->stream, g_err)) return rc;
+  } else {
+    int grid = (int)std::min<long long>(tiles, s->num_sms);
+    if (grid < 1) grid = 1;
+    k_decoder_simt<<<grid, kThreads, sizeof(SimtSmem), s->stream>>>(a);
+  }
+  if (s->timing) cudaEventRecord(next_event(s), s->stream);
+  s->ctr.kernel_launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+TermArgs base_term(DspgnSolver* s, int mode) {
+  TermArgs a{};
+  a.meta = s->d_meta; a.state = s->d_state.as<ObjState>(); a.decs = s->d_decs.as<DecoderDev>();
+  a.n_obj = s->n_obj; a.mode = mode;
+  a.pts = s->d_pts; a.pt_active = nullptr; a.rays = s->d_rays;
+  a.band_x = s->d_bx.as<float>(); a.band_s = s->d_bs.as<float>(); a.band_r = s->d_br.as<float>();
+  a.band_m = s->d_m.as<int>(); a.sdf_out = s->d_sdf.as<float>(); a.V_count = s->d_V.as<int>();
+  a.acc = s->d_acc.as<double>(); a.D = s->cfg.num_depth_samples;
+  a.dbg_J = nullptr; a.dbg_res = nullptr; a.dbg_obj = -1; a.dbg_P = 0;
+  return a;
+}
+
+int launch_init(DspgnSolver* s, int pose_only) {
+  InitArgs ia{};
+  ia.meta = s->d_meta; ia.state = s->d_state.as<ObjState>(); ia.T_init = s->d_Tinit; ia.code_init = s->d_code;
+  ia.acc = s->d_acc.as<double>(); ia.V_count = s->d_V.as<int>(); ia.band_m = s->d_m.as<int>();
+  ia.pt_active = nullptr; ia.n_obj = s->n_obj; ia.code_len = s->cfg.code_len; ia.D = s->cfg.num_depth_samples;
+  ia.pose_only = pose_only;
+  k_init<<<s->n_obj, 128, 0, s->stream>>>(ia);
+  s->ctr.kernel_launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// one GN iteration's residual-term kernels (everything before the solve)
+int launch_terms(DspgnSolver* s, int pose_only, float* dbg_J, float* dbg_res, int dbg_obj) {
+  const DspgnConfig& c = s->cfg;
+  {
+    TermArgs a = base_term(s, MODE_SDF);
+    a.huber_b = pose_only ? INFINITY : c.b2;       // optimizer.py:71 uses raw residuals
+    a.pose_only = pose_only;
+    a.dbg_J = dbg_J; a.dbg_res = dbg_res; a.dbg_obj = dbg_obj; a.dbg_P = pose_only ? 6 : 7 + c.code_len;
+    if (int rc = launch_term(s, a, s->tot_pts)) return rc;
+    s->ctr.rows_fwd_bwd += s->tot_pts;
+  }
+  if (!pose_only && !c.sdf_only) {
+    TermArgs f = base_term(s, MODE_RAYFWD);
+    if (int rc = launch_term(s, f, s->tot_smp)) return rc;
+    s->ctr.rows_fwd_only += s->tot_smp;
+    ScanArgs sa{};
+    sa.meta = s->d_meta; sa.state = s->d_state.as<ObjState>(); sa.rays = s->d_rays; sa.depth_fg = s->d_depth;
+    sa.sdf = s->d_sdf.as<float>(); sa.band_x = s->d_bx.as<float>(); sa.band_s = s->d_bs.as<float>();
+    sa.band_r = s->d_br.as<float>(); sa.band_m = s->d_m.as<int>(); sa.th = c.cut_off; sa.D = c.num_depth_samples;
+    sa.n_obj = s->n_obj;
+    k_ray_scan<<<s->n_obj, kScanThreads, 0, s->stream>>>(sa);
+    s->ctr.kernel_launches++;
+    CU(cudaGetLastError());
+    TermArgs b = base_term(s, MODE_BAND);
+    b.huber_b = c.b1;
+    if (int rc = launch_term(s, b, s->tot_smp)) return rc;
+  }
+  return 0;
+}
+
+SolveArgs base_solve(DspgnSolver* s, int pose_only) {
+  const DspgnConfig& c = s->cfg;
+  SolveArgs v{};
+  v.meta = s->d_meta; v.state = s->d_state.as<ObjState>(); v.acc = s->d_acc.as<double>();
+  v.V_count = s->d_V.as<int>(); v.band_m = s->d_m.as<int>();
+  v.prm = SolverParams{c.k1, c.k2, c.k3, c.k4, c.b1, c.b2, c.lr, c.s_damp, c.code_len, c.num_depth_samples, c.cut_off, c.sdf_only};
+  v.n_obj = s->n_obj; v.pose_only = pose_only; v.results = s->d_results.as<float>();
+  v.dbg_obj = -1; v.dbg_H = nullptr; v.dbg_b = nullptr; v.dbg_dx = nullptr; v.dbg_loss = nullptr;
+  return v;
+}
+
+}  // namespace
+
+int dspgn_run_batch(DspgnSolver* s, int mode) {
+  if (!s) return fail(DSPGN_E_ARG, "null solver");
+  if (s->n_obj < 1) return fail(DSPGN_E_ARG, "no batch uploaded");
+  if (mode != 0 && mode != 1) return fail(DSPGN_E_ARG, "mode must be 0 or 1");
+  CU(cudaSetDevice(s->device));
+  const int pose_only = mode;
+  const int iters = pose_only ? s->cfg.pose_only_iterations : s->cfg.num_iterations;
+  s->ctr = DspgnCounters{};
+  s->ev_used = 0;
+  CU(cudaEventRecord(s->ev_run0, s->stream));
+  if (int rc = launch_init(s, pose_only)) return rc;
+  for (int e = 0; e < iters; ++e) {
+    if (int rc = launch_terms(s, pose_only, nullptr, nullptr, -1)) return rc;
+    SolveArgs v = base_solve(s, pose_only);
+    v.last_iter = (e == iters - 1); v.iter_index = e;
+    k_solve<<<s->n_obj, kSolveThreads, 0, s->stream>>>(v);
+    s->ctr.kernel_launches++;
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(s->ev_run1, s->stream));
+  return 0;
+}
+
+const float* dspgn_results_device(DspgnSolver* s) { return s ? s->d_results.as<float>() : nullptr; }
+
+int dspgn_results(DspgnSolver* s, DspgnObjectOut* out) {
+  if (!s || !out) return fail(DSPGN_E_ARG, "null argument");
+  CU(cudaSetDevice(s->device));
+  static_assert(sizeof(DspgnObjectOut) == 4 * DSPGN_RESULT_FLOATS, "result record layout");
+  const size_t bytes = sizeof(DspgnObjectOut) * (size_t)s->n_obj;
+  CU(cudaMemcpyAsync(s->h_results.p, s->d_results.p, bytes, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  memcpy(out, s->h_results.p, bytes);
+  if (s->timing) {
+    float dec = 0.f;
+    for (size_t i = 0; i + 1 < s->ev_used; i += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]); dec += ms; }
+    s->ctr.decoder_ms = dec;
+  }
+  float tot = 0.f;
+  if (cudaEventElapsedTime(&tot, s->ev_run0, s->ev_run1) == cudaSuccess) s->ctr.total_ms = tot; else cudaGetLastError();
+  return 0;
+}
+
+int dspgn_reconstruct_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, DspgnObjectOut* out) {
+  if (int rc = dspgn_upload_batch(s, n_obj, in)) return rc;
+  if (int rc = dspgn_run_batch(s, 0)) return rc;
+  return dspgn_results(s, out);
+}
+
+int dspgn_estimate_pose_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, DspgnObjectOut* out) {
+  if (!s || !in) return fail(DSPGN_E_ARG, "null argument");
+  for (int o = 0; o < n_obj; ++o)
+    if (!in[o].code || !(in[o].scale > 0.f)) return fail(DSPGN_E_ARG, "estimate_pose needs a code and a positive scale per object");
+  if (int rc = dspgn_upload_batch(s, n_obj, in)) return rc;
+  if (int rc = dspgn_run_batch(s, 1)) return rc;
+  return dspgn_results(s, out);
+}
+
+int dspgn_decode_sdf(DspgnSolver* s, int class_id, const float* code, const float* x, int n, int x_rs, int x_cs,
+                     float* sdf_out) {
+  if (!s || !code || !x || !sdf_out || n < 1) return fail(DSPGN_E_ARG, "bad argument");
+  const float I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  DspgnObjectIn in{};
+  in.t_cam_obj = I4; in.t_rs = 4; in.t_cs = 1;
+  in.pts = x; in.n_pts = n; in.pts_rs = x_rs; in.pts_cs = x_cs;
+  in.rays = nullptr; in.n_rays = 0; in.depth = nullptr; in.n_depth = 0;
+  in.code = code; in.scale = 1.f; in.class_id = class_id;
+  if (int rc = dspgn_upload_batch(s, 1, &in)) return rc;
+  if (s->d_sdf.reserve(4 * (size_t)n)) return fail(DSPGN_E_ALLOC, "cudaMalloc");
+  s->ctr = DspgnCounters{};
+  s->ev_used = 0;
+  if (int rc = launch_init(s, 0)) return rc;
+  TermArgs a = base_term(s, MODE_PTSFWD);
+  if (int rc = launch_term(s, a, n)) return rc;
+  s->ctr.rows_fwd_only += n;
+  CU(cudaMemcpyAsync(sdf_out, s->d_sdf.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int dspgn_debug_system(DspgnSolver* s, int obj, int mode, float* H, float* b, float* dx, float* J_rows,
+                       float* res_rows, float* losses) {
+  if (!s || !H || !b || !dx) return fail(DSPGN_E_ARG, "null argument");
+  if (obj < 0 || obj >= s->n_obj) return fail(DSPGN_E_ARG, "bad object index");
+  CU(cudaSetDevice(s->device));
+  const int pose_only = mode;
+  const int P = pose_only ? 6 : 7 + s->cfg.code_len;
+  const int npts = s->h_meta[obj].n_pts;
+  DevBuf dJ;
+  if (dJ.reserve(4 * ((size_t)npts * P + npts))) return fail(DSPGN_E_ALLOC, "cudaMalloc");
+  float* dJp = dJ.as<float>();
+  float* dres = dJp + (size_t)npts * P;
+  s->ctr = DspgnCounters{};
+  s->ev_used = 0;
+  int rc = launch_init(s, pose_only);
+  if (!rc) rc = launch_terms(s, pose_only, dJp, dres, obj);
+  if (!rc) {
+    SolveArgs v = base_solve(s, pose_only);
+    float* d = s->d_dbg.as<float>();
+    v.dbg_obj = obj; v.dbg_H = d; v.dbg_b = d + kPMax * kPMax; v.dbg_dx = v.dbg_b + kPMax; v.dbg_loss = v.dbg_dx + kPMax;
+    v.last_iter = 0; v.iter_index = 0;
+    cudaMemsetAsync(d, 0, 4 * ((size_t)kPMax * kPMax + 2 * kPMax + 8), s->stream);
+    k_solve<<<s->n_obj, kSolveThreads, 0, s->stream>>>(v);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(DSPGN_E_CUDA, "k_solve launch failed");
+    if (!rc) {
+      cudaMemcpyAsync(H, v.dbg_H, 4 * (size_t)P * P, cudaMemcpyDeviceToHost, s->stream);
+      cudaMemcpyAsync(b, v.dbg_b, 4 * (size_t)P, cudaMemcpyDeviceToHost, s->stream);
+      cudaMemcpyAsync(dx, v.dbg_dx, 4 * (size_t)P, cudaMemcpyDeviceToHost, s->stream);
+      if (losses) cudaMemcpyAsync(losses, v.dbg_loss, 16, cudaMemcpyDeviceToHost, s->stream);
+      if (J_rows) cudaMemcpyAsync(J_rows, dJp, 4 * (size_t)npts * P, cudaMemcpyDeviceToHost, s->stream);
+      if (res_rows) cudaMemcpyAsync(res_rows, dres, 4 * (size_t)npts, cudaMemcpyDeviceToHost, s->stream);
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  dJ.release();
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(DSPGN_E_CUDA, std::string("debug_system: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+// Shared device-side structures and small closed forms for libdspgn (sm_100a).
+// Reference arithmetic being restated is cited per function (paths relative to the DSP-SLAM repo).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/dspgn.h"
+
+namespace dspgn {
+
+constexpr int kMaxCode = DSPGN_MAX_CODE;       // 64
+constexpr int kPInt = 72;                      // internal Jacobian row stride: [code 0..63 | pose 64..70 | pad]
+constexpr int kAccStride = kPInt * kPInt + kPInt + 8;  // doubles per (object, term): H | b | {loss_sum, rows, ...}
+constexpr int kAccB = kPInt * kPInt;
+constexpr int kAccLoss = kAccB + kPInt;        // +0 loss sum, +1 row count (double)
+constexpr int kTermSdf = 0, kTermRender = 1;
+
+// Static description of one object of the resident batch.
+struct ObjMeta {
+  int pts_off, n_pts;          // into pts (xyz interleaved)
+  int ray_off, n_rays, n_fg;   // into rays (xyz interleaved); depth_fg offset = fg_off
+  int fg_off;
+  int smp_off;                 // into per-sample buffers (n_rays * D)
+  int class_id;
+  float scale;                 // estimate_pose only
+  int has_code;
+};
+
+// Evolving per-object GN state (device resident for all iterations).
+struct ObjState {
+  float T_oc[12];              // [R|t] rows, object <- camera (R carries 1/scale)
+  float z[kMaxCode];
+  float dmin, dmax, dstep, dfar;   // optimizer.py:120-126
+  float loss;
+  int status;
+  int iters;
+  int V, m;                    // last render counters
+  int n_active;                // pose-only inlier count (optimizer.py:76-78)
+};
+
+struct SolverParams {
+  float k1, k2, k3, k4, b1, b2, lr, s_damp;
+  int code_len, D;
+  float th;
+  int sdf_only;
+};
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float huber_weight(float a_abs, float b) {
+  // loss_utils.py:236-247: w = sqrt(rho)/a; rho = a^2 (a<=b) else 2ba-b^2; a==0 -> 0
+  float rho = (a_abs <= b) ? a_abs * a_abs : (2.0f * b * a_abs - b * b);
+  float den = (a_abs == 0.0f) ? 1.0f : a_abs;
+  return sqrtf(rho) / den;
+}
+
+__device__ __forceinline__ float occupancy(float s, float th) {
+  // loss_utils.py:40-48
+  float c = fminf(fmaxf(s, -th), th);
+  return 0.5f - c / (2.0f * th);
+}
+
+__device__ __forceinline__ float lin_depth(float dmin, float dmax, float step, int j, int D) {
+  // torch.linspace fp32 (optimizer.py:124): symmetric halves, start + step*i as one fused multiply-add
+  return (j < D / 2) ? __fmaf_rn(step, (float)j, dmin) : __fmaf_rn(-step, (float)(D - 1 - j), dmax);
+}
+
+__device__ __forceinline__ void xform_point(const float* __restrict__ T, float px, float py, float pz,
+                                            float& ox, float& oy, float& oz) {
+  // loss.py:31-32: products rounded, then summed left to right, then + t (as torch does it)
+  ox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, T[0]), __fmul_rn(py, T[1])), __fmul_rn(pz, T[2])), T[3]);
+  oy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, T[4]), __fmul_rn(py, T[5])), __fmul_rn(pz, T[6])), T[7]);
+  oz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, T[8]), __fmul_rn(py, T[9])), __fmul_rn(pz, T[10])), T[11]);
+}
+
+// 3x4 [A|t] -> inverse [A^-1 | -A^-1 t] (adjugate, fp64 inside, fp32 out)
+__device__ inline void inv_affine(const float* T, float* out, double* det_out) {
+  double a = T[0], b = T[1], c = T[2], d = T[4], e = T[5], f = T[6], g = T[8], h = T[9], i = T[10];
+  double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+  double det = a * A + b * B + c * C;
+  double id = 1.0 / det;
+  double m[9] = {A * id, (c * h - b * i) * id, (b * f - c * e) * id,
+                 B * id, (a * i - c * g) * id, (c * d - a * f) * id,
+                 C * id, (b * g - a * h) * id, (a * e - b * d) * id};
+  double tx = T[3], ty = T[7], tz = T[11];
+  for (int r = 0; r < 3; ++r) {
+    out[r * 4 + 0] = (float)m[r * 3 + 0];
+    out[r * 4 + 1] = (float)m[r * 3 + 1];
+    out[r * 4 + 2] = (float)m[r * 3 + 2];
+    out[r * 4 + 3] = (float)(-(m[r * 3 + 0] * tx + m[r * 3 + 1] * ty + m[r * 3 + 2] * tz));
+  }
+  if (det_out) *det_out = det;
+}
+
+// optimizer.py:120-126: depth range from the current pose.
+__device__ inline void derive_depth_range(ObjState& st, int D) {
+  float Tco[12];
+  double det_oc;
+  inv_affine(st.T_oc, Tco, &det_oc);
+  float det_co = (float)(1.0 / det_oc);
+  float scale = powf(det_co, 1.0f / 3.0f);
+  st.dmin = Tco[11] - scale;
+  st.dmax = Tco[11] + scale;
+  st.dstep = (st.dmax - st.dmin) / (float)(D - 1);
+  st.dfar = 1.1f * st.dmax;
+}
+
+// loss_utils.py:188-233 (Sim(3)) / 129-163 (SE(3), s ignored, J without scale terms).
+__device__ inline void exp_sim3_dev(const float* x, bool sim3, float* out /*3x4*/) {
+  float v0 = x[0], v1 = x[1], v2 = x[2], w0 = x[3], w1 = x[4], w2 = x[5];
+  float s = sim3 ? x[6] : 0.0f;
+  float W[9] = {0.f, -w2, w1, w2, 0.f, -w0, -w1, w0, 0.f};
+  float W2[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      W2[r * 3 + c] = W[r * 3 + 0] * W[0 * 3 + c] + W[r * 3 + 1] * W[1 * 3 + c] + W[r * 3 + 2] * W[2 * 3 + c];
+  float theta = sqrtf(w0 * w0 + w1 * w1 + w2 * w2);
+  float th2 = theta * theta;
+  float es = sim3 ? expf(s) : 1.0f;
+  float R[9], J[9];
+  const float I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (theta <= 1e-8f) {
+    float c = 1.0f;
+    if (sim3 && s != 0.0f) c = (es - 1.0f) / s;
+    for (int k = 0; k < 9; ++k) { R[k] = I[k]; J[k] = c * I[k]; }
+  } else {
+    float sn = sinf(theta), cs = cosf(theta);
+    float ra = sn / theta, rb = (1.0f - cs) / th2;
+    for (int k = 0; k < 9; ++k) R[k] = I[k] + W[k] * ra + W2[k] * rb;
+    if (sim3) {
+      float a = es * sn, b = es * cs;
+      float c = (s <= 1e-8f) ? 0.0f : (es - 1.0f) / s;      // loss_utils.py:223 quirk kept
+      float den = s * s + th2;
+      float k1 = (a * s + (1.0f - b) * theta) / den;
+      float k2 = c - ((b - 1.0f) * s + a * theta) / den;
+      for (int k = 0; k < 9; ++k) J[k] = c * I[k] + (k1 / theta) * W[k] + (k2 / th2) * W2[k];
+    } else {
+      float k1 = (1.0f - cs) / th2;
+      float k2 = (theta - sn) / (th2 * theta);
+      for (int k = 0; k < 9; ++k) J[k] = I[k] + k1 * W[k] + k2 * W2[k];
+    }
+  }
+  for (int r = 0; r < 3; ++r) {
+    out[r * 4 + 0] = es * R[r * 3 + 0];
+    out[r * 4 + 1] = es * R[r * 3 + 1];
+    out[r * 4 + 2] = es * R[r * 3 + 2];
+    out[r * 4 + 3] = J[r * 3 + 0] * v0 + J[r * 3 + 1] * v1 + J[r * 3 + 2] * v2;
+  }
+}
+
+// out = A * B for 3x4 affine matrices (implicit last row 0 0 0 1), fp32 like torch.mm
+__device__ inline void mul_affine(const float* A, const float* B, float* out) {
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 4; ++c) {
+      float acc = A[r * 4 + 0] * B[0 * 4 + c] + A[r * 4 + 1] * B[1 * 4 + c] + A[r * 4 + 2] * B[2 * 4 + c];
+      if (c == 3) acc += A[r * 4 + 3];
+      out[r * 4 + c] = acc;
+    }
+  }
+}
+
+__device__ __forceinline__ void atomic_add_f64(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+}  // namespace dspgn

@@ -1,0 +1,394 @@
+// Per-object kernels: state initialisation, normal-equation assembly + solve + Sim(3)/SE(3) update,
+// and the per-ray occupancy scan / band compaction of the render term.
+// Restates optimizer.py:45-86, 97-203; loss.py:84-141, 155-178; loss_utils.py:188-233.
+#pragma once
+#include "dspgn_common.cuh"
+
+namespace dspgn {
+
+struct InitArgs {
+  const ObjMeta* meta;
+  ObjState* state;
+  const float* T_init;     // [n_obj][16] row-major object->camera
+  const float* code_init;  // [n_obj][64]
+  double* acc;             // zeroed here
+  int* V_count;
+  int* band_m;
+  uint8_t* pt_active;      // [total_pts] reset to 1 (pose-only mode)
+  int n_obj, code_len, D, pose_only;
+};
+
+__global__ void k_init(InitArgs a) {
+  const int o = blockIdx.x, tid = threadIdx.x;
+  ObjState& st = a.state[o];
+  const ObjMeta M = a.meta[o];
+  double* acc = a.acc + (size_t)o * 2 * kAccStride;
+  for (int i = tid; i < 2 * kAccStride; i += blockDim.x) acc[i] = 0.0;
+  if (a.pt_active != nullptr)
+    for (int i = tid; i < M.n_pts; i += blockDim.x) a.pt_active[M.pts_off + i] = 1;
+  if (tid < kMaxCode) st.z[tid] = (M.has_code && tid < a.code_len) ? a.code_init[o * kMaxCode + tid] : 0.f;
+  if (tid == 0) {
+    float Tco[12];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) Tco[r * 4 + c] = a.T_init[o * 16 + r * 4 + c];
+    if (a.pose_only)                       // optimizer.py:54: t_cam_obj[:3,:3] *= scale
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) Tco[r * 4 + c] *= M.scale;
+    inv_affine(Tco, st.T_oc, nullptr);     // optimizer.py:55 / :104
+    derive_depth_range(st, a.D);
+    st.loss = 0.f; st.status = 0; st.iters = 0; st.V = 0; st.m = 0; st.n_active = M.n_pts;
+    a.V_count[o] = 0;
+    a.band_m[o] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct SolveArgs {
+  const ObjMeta* meta;
+  ObjState* state;
+  double* acc;
+  int* V_count;
+  int* band_m;
+  SolverParams prm;
+  int n_obj;
+  int pose_only;          // estimate_pose_cam_obj variant
+  int last_iter;          // write the result record
+  int iter_index;
+  float* results;         // [n_obj][DSPGN_RESULT_FLOATS]
+  // debug: dump the system of object dbg_obj and do not update any state
+  int dbg_obj; float* dbg_H; float* dbg_b; float* dbg_dx; float* dbg_loss;
+};
+
+constexpr int kSolveThreads = 128;
+constexpr int kPMax = 7 + kMaxCode;   // 71
+
+__device__ __forceinline__ int ext_to_int(int e, int npose, int L) {
+  // external order [pose | code]  ->  internal rows [code 0..63 | pose 64..70]
+  return (e < npose) ? (kMaxCode + e) : (e - npose);
+}
+
+__device__ void write_result(const SolveArgs& a, int o, const ObjState& st) {
+  float* r = a.results + (size_t)o * DSPGN_RESULT_FLOATS;
+  float Tco[12];
+  inv_affine(st.T_oc, Tco, nullptr);                     // optimizer.py:200 / :83
+  if (a.pose_only) {                                     // optimizer.py:84: t_cam_obj[:3,:3] /= scale
+    const float s = a.meta[o].scale;
+    for (int i = 0; i < 3; ++i)
+      for (int c = 0; c < 3; ++c) Tco[i * 4 + c] /= s;
+  }
+  for (int i = 0; i < 12; ++i) r[i] = Tco[i];
+  r[12] = 0.f; r[13] = 0.f; r[14] = 0.f; r[15] = 1.f;
+  for (int i = 0; i < kMaxCode; ++i) r[16 + i] = st.z[i];
+  r[80] = st.loss;
+  reinterpret_cast<int*>(r)[81] = st.status;
+  reinterpret_cast<int*>(r)[82] = st.V;
+  reinterpret_cast<int*>(r)[83] = st.m;
+  reinterpret_cast<int*>(r)[84] = st.iters;
+  reinterpret_cast<int*>(r)[85] = 0;
+}
+
+__global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
+  __shared__ double Hs[kPMax * kPMax];
+  __shared__ double bs[kPMax];
+  __shared__ double dxs[kPMax];
+  __shared__ int s_flag;
+  const int o = blockIdx.x, tid = threadIdx.x;
+  ObjState& st = a.state[o];
+  const SolverParams& prm = a.prm;
+  const int L = prm.code_len;
+  const int npose = a.pose_only ? 6 : 7;
+  const int P = a.pose_only ? 6 : (7 + L);
+  double* accS = a.acc + ((size_t)o * 2 + kTermSdf) * kAccStride;
+  double* accR = a.acc + ((size_t)o * 2 + kTermRender) * kAccStride;
+  const bool dbg = (a.dbg_H != nullptr);
+
+  if (st.status != 0) {                          // frozen object: keep its record
+    if (a.last_iter && tid == 0 && !dbg) write_result(a, o, st);
+    return;
+  }
+  // ---- losses and the reference's soft-failure exits (optimizer.py:130-150) -----------------
+  const double nS = accS[kAccLoss + 1];
+  const float sdf_loss = (float)(accS[kAccLoss] / nS);
+  const int V = a.V_count[o], m = a.band_m[o];
+  float render_loss = 0.f;
+  int status = 0;
+  const bool use_render = !a.pose_only && !prm.sdf_only;
+  if (isnan(sdf_loss)) status = DSPGN_ST_SDF_NAN;
+  else if (use_render) {
+    if (V < 10) status = DSPGN_ST_RENDER_FEW;
+    else {
+      render_loss = (m > 0) ? (float)(accR[kAccLoss] / (double)m) : NAN;
+      if (isnan(render_loss)) status = DSPGN_ST_RENDER_NAN;
+    }
+  }
+  if (dbg && o == a.dbg_obj && tid == 0) {
+    a.dbg_loss[0] = sdf_loss; a.dbg_loss[1] = render_loss; a.dbg_loss[2] = (float)V; a.dbg_loss[3] = (float)m;
+  }
+  if (status != 0) {
+    __syncthreads();
+    if (!dbg) {
+      if (tid == 0) { st.status = status; st.V = V; st.m = m; if (a.last_iter) write_result(a, o, st); }
+    }
+    return;
+  }
+  const float loss = prm.k1 * render_loss + prm.k2 * sdf_loss;     // optimizer.py:155
+
+  // ---- assemble H, b (optimizer.py:161-184; pose-only: optimizer.py:68-71) ------------------
+  const double wS = a.pose_only ? 1.0 / nS : (double)prm.k2 / nS;
+  const double wR = use_render ? (double)prm.k1 / (double)m : 0.0;
+  for (int idx = tid; idx < P * P; idx += kSolveThreads) {
+    const int r = idx / P, c = idx - r * P;
+    int ri = ext_to_int(r, npose, L), ci = ext_to_int(c, npose, L);
+    if (ri > ci) { int t = ri; ri = ci; ci = t; }          // accumulators hold the upper triangle
+    double h = wS * accS[ri * kPInt + ci];
+    if (use_render) h += wR * accR[ri * kPInt + ci];
+    Hs[idx] = h;
+  }
+  for (int r = tid; r < P; r += kSolveThreads) {
+    const int ri = ext_to_int(r, npose, L);
+    double v = -wS * accS[kAccB + ri];
+    if (use_render) v -= wR * accR[kAccB + ri];
+    bs[r] = v;
+  }
+  __syncthreads();
+  if (a.pose_only) {
+    if (tid < 6) Hs[tid * P + tid] += 1e-2;                              // optimizer.py:70
+  } else {
+    if (tid < L) {                                                       // optimizer.py:170-172
+      Hs[(7 + tid) * P + 7 + tid] += (double)prm.k3;
+      bs[7 + tid] -= (double)prm.k3 * (double)st.z[tid];
+    }
+    if (tid == 0) {
+      // rotation prior (loss.py:155-178): r = 1 - (R_co e_y).n_g, n_g = (0,-1,0)
+      float Tco[12];
+      double det_oc;
+      inv_affine(st.T_oc, Tco, &det_oc);
+      const float scale = powf((float)(1.0 / det_oc), 1.0f / 3.0f);
+      float rco[12];
+      for (int i = 0; i < 12; ++i) rco[i] = Tco[i] / scale;
+      rco[3] = rco[7] = rco[11] = 0.f;
+      float roc[12];
+      inv_affine(rco, roc, nullptr);
+      const float res_rot = 1.0f + rco[1 * 4 + 1];                     // 1 - dot(R_co[:,1], (0,-1,0))
+      if (!(res_rot < 1e-7f)) {
+        // v = R_oc n_g = -R_oc[:,1];  J_rot = v x e_y = (-v_z, 0, v_x)
+        const float vx = -roc[0 * 4 + 1], vz = -roc[2 * 4 + 1];
+        const double J[3] = {(double)(-vz), 0.0, (double)vx};
+        for (int u = 0; u < 3; ++u) {
+          for (int v = 0; v < 3; ++v) Hs[(3 + u) * P + 3 + v] += (double)prm.k4 * J[u] * J[v];
+          bs[3 + u] += (double)prm.k4 * J[u] * (double)res_rot;      // optimizer.py:177-179 sign
+        }
+      }
+      for (int u = 0; u < 7; ++u) Hs[u * P + u] += 1.0;               // optimizer.py:182
+      Hs[6 * P + 6] += (double)prm.s_damp;                            // optimizer.py:183
+    }
+  }
+  __syncthreads();
+  if (dbg && o == a.dbg_obj) {
+    for (int idx = tid; idx < P * P; idx += kSolveThreads) a.dbg_H[idx] = (float)Hs[idx];
+    for (int r = tid; r < P; r += kSolveThreads) a.dbg_b[r] = (float)bs[r];
+  }
+  __syncthreads();
+
+  // ---- Cholesky H = L L^T in fp64, in place (lower triangle), then two triangular solves --------
+  if (tid == 0) s_flag = 0;
+  __syncthreads();
+  for (int k = 0; k < P; ++k) {
+    if (tid == 0) {
+      const double d = Hs[k * P + k];
+      if (!(d > 0.0) || !isfinite(d)) { s_flag = 1; Hs[k * P + k] = 1.0; }
+      else Hs[k * P + k] = sqrt(d);
+    }
+    __syncthreads();
+    const double inv = 1.0 / Hs[k * P + k];
+    for (int i = k + 1 + tid; i < P; i += kSolveThreads) Hs[i * P + k] *= inv;
+    __syncthreads();
+    const int n = P - k - 1;
+    for (int idx = tid; idx < n * n; idx += kSolveThreads) {
+      const int i = k + 1 + idx / n, j = k + 1 + idx % n;
+      if (j <= i) Hs[i * P + j] -= Hs[i * P + k] * Hs[j * P + k];
+    }
+    __syncthreads();
+  }
+  if (tid < 32) {
+    // forward  L y = b, backward  L^T x = y  (one warp; dot products split over lanes)
+    const int lane = tid;
+    for (int i = 0; i < P; ++i) {
+      double s = 0.0;
+      for (int j = lane; j < i; j += 32) s += Hs[i * P + j] * dxs[j];
+      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+      if (lane == 0) dxs[i] = (bs[i] - s) / Hs[i * P + i];
+      __syncwarp();
+    }
+    for (int i = P - 1; i >= 0; --i) {
+      double s = 0.0;
+      for (int j = i + 1 + lane; j < P; j += 32) s += Hs[j * P + i] * dxs[j];
+      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+      if (lane == 0) dxs[i] = (dxs[i] - s) / Hs[i * P + i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < P; ++i) if (!isfinite(dxs[i])) s_flag = 1;
+  }
+  __syncthreads();
+  if (dbg) {
+    if (o == a.dbg_obj) for (int r = tid; r < P; r += kSolveThreads) a.dbg_dx[r] = (float)dxs[r];
+    return;
+  }
+  // ---- update (optimizer.py:186-192 / :72-74), clear accumulators, next depth range -----------
+  for (int i = tid; i < 2 * kAccStride; i += kSolveThreads) a.acc[(size_t)o * 2 * kAccStride + i] = 0.0;
+  if (!a.pose_only && tid < L && !s_flag) st.z[tid] += prm.lr * (float)dxs[tid + 7];
+  if (tid == 0) {
+    st.loss = loss; st.V = V; st.m = m;
+    a.V_count[o] = 0;
+    if (s_flag) {
+      st.status = DSPGN_ST_SOLVE;
+    } else {
+      float dp[7];
+      for (int i = 0; i < npose; ++i) dp[i] = (a.pose_only ? 1.0f : prm.lr) * (float)dxs[i];
+      float dT[12], Tn[12];
+      exp_sim3_dev(dp, !a.pose_only, dT);
+      mul_affine(dT, st.T_oc, Tn);
+      for (int i = 0; i < 12; ++i) st.T_oc[i] = Tn[i];
+      derive_depth_range(st, prm.D);
+      st.iters += 1;
+    }
+    if (a.last_iter) write_result(a, o, st);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Render term, per-ray part (loss.py:84-141).  One CTA per object, one warp per ray, two passes:
+// pass 1 counts the band samples each ray keeps, a block scan turns counts into row offsets, pass 2
+// recomputes and writes rows (x_o, de/ds, clamped depth residual) in (ray, sample) order -- the same
+// order torch.where yields, and deterministic.
+struct ScanArgs {
+  const ObjMeta* meta;
+  const ObjState* state;
+  const float* rays;
+  const float* depth_fg;
+  const float* sdf;       // per sample, +inf outside the unit sphere
+  float* band_x; float* band_s; float* band_r;
+  int* band_m;
+  float th;
+  int D;
+  int n_obj;
+};
+
+constexpr int kScanThreads = 1024;
+constexpr int kScanMaxRays = 8192;
+
+__device__ __forceinline__ void ray_scan(const ScanArgs& a, const ObjMeta& M, const ObjState& st, int ray, int lane,
+                                         bool keep[2], float de_ds[2], float& res) {
+  const int D = a.D;
+  const float th = a.th;
+  const float* srow = a.sdf + (size_t)M.smp_off + (size_t)ray * D;
+  float s[2], o[2], q[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = lane + 32 * h;
+    s[h] = (j < D) ? srow[j] : INFINITY;
+    o[h] = (j < D) ? occupancy(s[h], th) : 0.f;      // +inf -> clamp -> 0 (outside sphere: loss.py:84)
+    q[h] = 1.f - o[h];
+  }
+  // inclusive product scan over the 64 slots -> transmittance T_l (loss.py:99)
+  float t0 = q[0], t1 = q[1];
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float y0 = __shfl_up_sync(0xffffffffu, t0, d), y1 = __shfl_up_sync(0xffffffffu, t1, d);
+    if (lane >= d) { t0 *= y0; t1 *= y1; }
+  }
+  const float tot0 = __shfl_sync(0xffffffffu, t0, 31);
+  t1 *= tot0;
+  float T[2] = {t0, t1};
+  // termination probabilities and rendered depth (loss.py:100-114)
+  float Tprev0 = __shfl_up_sync(0xffffffffu, t0, 1);
+  float Tprev1 = __shfl_up_sync(0xffffffffu, t1, 1);
+  if (lane == 0) { Tprev0 = 1.f; Tprev1 = tot0; }
+  float du = 0.f;
+  if (lane < D) du += lin_depth(st.dmin, st.dmax, st.dstep, lane, D) * (o[0] * Tprev0);
+  if (lane + 32 < D) du += lin_depth(st.dmin, st.dmax, st.dstep, lane + 32, D) * (o[1] * Tprev1);
+  const int jl = D - 1;                                   // T_{D-1}
+  const float Tlast = __shfl_sync(0xffffffffu, (jl >= 32) ? T[1] : T[0], jl & 31);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) du += __shfl_xor_sync(0xffffffffu, du, d);
+  du += st.dfar * Tlast;
+  // suffix sums S_j = sum_{l >= j} T_l (loss.py:118-122); slots >= D contribute 0
+  float u0 = (lane < D) ? T[0] : 0.f, u1 = (lane + 32 < D) ? T[1] : 0.f;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float y0 = __shfl_down_sync(0xffffffffu, u0, d), y1 = __shfl_down_sync(0xffffffffu, u1, d);
+    if (lane + d < 32) { u0 += y0; u1 += y1; }
+  }
+  const float hi_tot = __shfl_sync(0xffffffffu, u1, 0);
+  u0 += hi_tot;
+  const float S[2] = {u0, u1};
+  const float delta_d = (st.dmax - st.dmin) / (float)(D - 1);
+  const float do_ds = -1.0f / (2.0f * th);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const bool band = (s[h] > -th) && (s[h] < th);      // loss.py:88 (strict); inf never passes
+    const float de_do = S[h] / (1.f - o[h]);
+    keep[h] = band && (de_do > 1e-2f);                  // loss.py:125
+    de_ds[h] = de_do * delta_d * do_ds;                 // loss.py:128-130
+  }
+  const float dobs = (ray < M.n_fg) ? a.depth_fg[M.fg_off + ray] : st.dfar;   // optimizer.py:126
+  res = fminf(fmaxf(dobs - du, -0.3f), 0.3f);           // loss.py:136-141
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_ray_scan(ScanArgs a) {
+  __shared__ int s_cnt[kScanMaxRays];
+  __shared__ int s_wsum[32];
+  const int o = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = kScanThreads / 32;
+  const ObjMeta M = a.meta[o];
+  const ObjState& st = a.state[o];
+  if (st.status != 0) return;
+  const int N = M.n_rays;
+  bool keep[2]; float de_ds[2]; float res;
+  for (int ray = warp; ray < N; ray += nw) {
+    ray_scan(a, M, st, ray, lane, keep, de_ds, res);
+    const int c = __popc(__ballot_sync(0xffffffffu, keep[0])) + __popc(__ballot_sync(0xffffffffu, keep[1]));
+    if (lane == 0) s_cnt[ray] = c;
+  }
+  __syncthreads();
+  // block exclusive scan of s_cnt[0..N)
+  int carry = 0;
+  for (int base = 0; base < N; base += kScanThreads) {
+    const int i = base + tid;
+    const int v = (i < N) ? s_cnt[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) s_wsum[warp] = x;
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) { if (w < warp) woff += s_wsum[w]; tot += s_wsum[w]; }
+    if (i < N) s_cnt[i] = carry + woff + x - v;
+    carry += tot;
+    __syncthreads();
+  }
+  if (tid == 0) a.band_m[o] = carry;
+  for (int ray = warp; ray < N; ray += nw) {
+    ray_scan(a, M, st, ray, lane, keep, de_ds, res);
+    const unsigned b0 = __ballot_sync(0xffffffffu, keep[0]), b1 = __ballot_sync(0xffffffffu, keep[1]);
+    const int base = s_cnt[ray];
+    const float* q = a.rays + 3 * (size_t)(M.ray_off + ray);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (!keep[h]) continue;
+      const int j = lane + 32 * h;
+      const int pos = base + (h == 0 ? __popc(b0 & ((1u << lane) - 1u)) : __popc(b0) + __popc(b1 & ((1u << lane) - 1u)));
+      const float d = lin_depth(st.dmin, st.dmax, st.dstep, j, a.D);
+      float x, y, z;
+      xform_point(st.T_oc, __fmul_rn(q[0], d), __fmul_rn(q[1], d), __fmul_rn(q[2], d), x, y, z);
+      const size_t row = (size_t)M.smp_off + pos;
+      a.band_x[3 * row] = x; a.band_x[3 * row + 1] = y; a.band_x[3 * row + 2] = z;
+      a.band_s[row] = de_ds[h];
+      a.band_r[row] = res;
+    }
+  }
+}
+
+}  // namespace dspgn

@@ -1,0 +1,169 @@
+/*
+ * dspgn.h -- C ABI of libdspgn.so: DSP-SLAM's per-object shape-prior Gauss-Newton reconstruction
+ * as hand-written CUDA for NVIDIA B200 (sm_100a).
+ *
+ * Drop-in boundary.  The reference has no native FFI for this path: its C++ LocalMapping thread
+ * calls Python through pybind11 (src/LocalMapping.cc:38-40, src/LocalMapping_util.cc:109-110,
+ * 179-181, 390-392), and Python issues PyTorch ops.  The entry points below are what a native
+ * binding for exactly those calls binds to; dsp_slam_b200/optimizer.py (ctypes) is that binding,
+ * and INTEGRATION.md shows the one-file replacement of reconstruct/optimizer.py.
+ *
+ *   reference call                                            entry point here
+ *   --------------------------------------------------------  -------------------------------
+ *   reconstruct.utils.get_decoder (deep_sdf/workspace.py:202)  dspgn_decoder_create
+ *   Optimizer.__init__           (reconstruct/optimizer.py:27)  dspgn_solver_create
+ *   Optimizer.reconstruct_object (reconstruct/optimizer.py:88)  dspgn_reconstruct_batch
+ *   Optimizer.estimate_pose_cam_obj (optimizer.py:45)           dspgn_estimate_pose_batch
+ *   loss_utils.decode_sdf        (reconstruct/loss_utils.py:51) dspgn_decode_sdf
+ *   loss.compute_sdf_loss / compute_render_loss (loss.py:22,46) dspgn_debug_system (test hook)
+ *
+ * Conventions: every function returns 0 on success or a negative DSPGN_E_* code; per-object soft
+ * failures (the reference's is_good=False exits, optimizer.py:130-150) are reported in
+ * DspgnObjectOut.status and never through the return code; nothing throws across this ABI.
+ * All host buffers are caller-owned, plain float32/int32 with explicit element strides (so the
+ * column-major arrays pybind11's Eigen casters produce need no host-side transpose); device
+ * buffers are owned by the handles.  One solver = one GPU = one host thread at a time.
+ */
+#ifndef DSPGN_H_
+#define DSPGN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSPGN_MAX_CODE 64
+#define DSPGN_MAX_LINEAR 12
+#define DSPGN_MAX_CLASSES 4
+
+/* return codes */
+#define DSPGN_OK 0
+#define DSPGN_E_ARG (-1)      /* bad argument / unsupported decoder shape */
+#define DSPGN_E_CUDA (-2)     /* CUDA runtime error; see dspgn_last_error() */
+#define DSPGN_E_NOGPU (-3)    /* no usable sm_100 device */
+#define DSPGN_E_ALLOC (-4)
+
+/* DspgnObjectOut.status (per-object soft failure = the reference's is_good=False exits) */
+#define DSPGN_ST_OK 0
+#define DSPGN_ST_SDF_NAN 1     /* optimizer.py:135-136 */
+#define DSPGN_ST_RENDER_FEW 2  /* loss.py:72-73 (fewer than 10 samples in the unit sphere) */
+#define DSPGN_ST_RENDER_NAN 3  /* optimizer.py:149-150 (no band rows -> NaN loss) */
+#define DSPGN_ST_SOLVE 4       /* normal matrix not positive definite / non-finite step */
+
+/* decoder engines */
+#define DSPGN_ENGINE_AUTO 0
+#define DSPGN_ENGINE_SIMT 1    /* fp32 FFMA kernels: on-device ground truth */
+#define DSPGN_ENGINE_TC 2      /* tcgen05 tensor-core kernels, 3-pass split-fp16 (fp32-class accuracy) */
+
+typedef struct DspgnDecoder DspgnDecoder;
+typedef struct DspgnSolver DspgnSolver;
+
+/* A DeepSDF decoder (deep_sdf/deep_sdf_decoder.py:29-63) with weight-norm already folded:
+ * layer k is  y = W[k] x + b[k],  W[k] row-major (out_dim[k], in_dim[k]);
+ * ReLU after every layer but the last, tanh after the last (deep_sdf_decoder.py:103-108);
+ * at layer `latent_in_layer` the (latent_size+3)-wide input is concatenated after the
+ * activations (deep_sdf_decoder.py:87-88); -1 = none. */
+typedef struct {
+  int32_t latent_size;
+  int32_t num_linear;
+  int32_t in_dim[DSPGN_MAX_LINEAR];
+  int32_t out_dim[DSPGN_MAX_LINEAR];
+  int32_t latent_in_layer;
+} DspgnDecoderSpec;
+
+/* The `optimizer` block of configs/config_*.json as read by reconstruct/optimizer.py:27-43. */
+typedef struct {
+  float k1, k2, k3, k4;        /* joint_optim.k1..k4 */
+  float b1, b2;                /* Huber thresholds: render, sdf */
+  float lr;                    /* joint_optim.learning_rate */
+  float s_damp;                /* joint_optim.scale_damping */
+  int32_t num_iterations;      /* joint_optim.num_iterations */
+  int32_t code_len;            /* 32 or 64 (<= latent_size of the decoders) */
+  int32_t num_depth_samples;   /* D, <= 64 */
+  float cut_off;               /* cut_off_threshold */
+  int32_t pose_only_iterations;/* pose_only_optim.num_iterations */
+  int32_t sdf_only;            /* 1: skip the render term (BASELINE config 2 "surface-SDF loss") */
+  int32_t engine;              /* DSPGN_ENGINE_* */
+} DspgnConfig;
+
+/* One detection, host side.  Strides are in elements (floats). */
+typedef struct {
+  const float* t_cam_obj; int32_t t_rs, t_cs;           /* (4,4) object->camera, Sim(3) */
+  const float* pts;  int32_t n_pts;  int32_t pts_rs, pts_cs;    /* (n_pts,3) camera frame */
+  const float* rays; int32_t n_rays; int32_t rays_rs, rays_cs;  /* (n_rays,3), foreground first */
+  const float* depth; int32_t n_depth;                  /* (n_depth,) foreground depths */
+  const float* code;                                    /* (code_len,) initial code or NULL = zeros */
+  float scale;                                          /* estimate_pose only: object scale */
+  int32_t class_id;                                     /* index into the solver's decoder list */
+} DspgnObjectIn;
+
+typedef struct {
+  float t_cam_obj[16];            /* row-major (4,4); undefined when status != 0 */
+  float code[DSPGN_MAX_CODE];
+  float loss;                     /* k1*render + k2*sdf of the last evaluated iteration */
+  int32_t status;                 /* DSPGN_ST_* */
+  int32_t n_valid;                /* V: ray samples inside the unit sphere, last iteration */
+  int32_t n_band;                 /* m: band rows kept, last iteration */
+  int32_t iters_done;
+  int32_t pad_[3];
+} DspgnObjectOut;                 /* 88 floats */
+
+/* device-side result record (same layout), for callers that keep results on the GPU */
+#define DSPGN_RESULT_FLOATS 88
+
+const char* dspgn_last_error(void);
+int dspgn_version(void);
+
+int dspgn_decoder_create(const DspgnDecoderSpec* spec, const float* const* W, const float* const* b,
+                         int device, DspgnDecoder** out);
+void dspgn_decoder_destroy(DspgnDecoder* dec);
+
+int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, int n_classes,
+                        int device, DspgnSolver** out);
+void dspgn_solver_destroy(DspgnSolver* s);
+/* stream = a cudaStream_t (NULL = legacy default stream). Work is enqueued on it. */
+int dspgn_solver_set_stream(DspgnSolver* s, void* cuda_stream);
+int dspgn_solver_engine(const DspgnSolver* s);   /* resolved DSPGN_ENGINE_* */
+
+/* Whole call, host buffers in, host buffers out (upload + all GN iterations + download + sync). */
+int dspgn_reconstruct_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, DspgnObjectOut* out);
+int dspgn_estimate_pose_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, DspgnObjectOut* out);
+
+/* The same split into its three phases, for callers that keep a batch resident in HBM:
+ *   upload:  pack + H2D of the batch into the solver's workspace (async on the stream)
+ *   run:     reset state from the uploaded initial poses/codes, run all GN iterations (async);
+ *            mode 0 = joint (reconstruct_object), 1 = pose-only (estimate_pose_cam_obj)
+ *   results: D2H + stream sync;  results_device: pointer to n_obj*DSPGN_RESULT_FLOATS floats */
+int dspgn_upload_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in);
+int dspgn_run_batch(DspgnSolver* s, int mode);
+int dspgn_results(DspgnSolver* s, DspgnObjectOut* out);
+const float* dspgn_results_device(DspgnSolver* s);
+
+/* Forward-only decode (loss_utils.decode_sdf): x (n,3) host, strides in elements -> sdf (n,) host. */
+int dspgn_decode_sdf(DspgnSolver* s, int class_id, const float* code, const float* x, int n,
+                     int x_rs, int x_cs, float* sdf_out);
+
+/* Counters of the last run (for roofline arithmetic): decoder rows evaluated fwd+bwd and fwd-only,
+ * and the number of kernel launches issued. */
+typedef struct {
+  int64_t rows_fwd_bwd;
+  int64_t rows_fwd_only;
+  int64_t kernel_launches;
+  float decoder_ms;      /* device time of the decoder kernels of the last run (CUDA events), if timed */
+  float total_ms;
+} DspgnCounters;
+int dspgn_counters(DspgnSolver* s, DspgnCounters* out);
+int dspgn_enable_timing(DspgnSolver* s, int on);
+
+/* Test hook: evaluate one GN iteration at the uploaded initial state of object `obj` WITHOUT
+ * updating it and return the assembled system: H (P*P row-major), b (P), dx (P), P = 7+code_len
+ * (mode 0) or 6 (mode 1); J_rows/res_rows (may be NULL): the SDF-term Jacobian rows (n_pts,P) and
+ * residuals (n_pts) as loss.compute_sdf_loss returns them. */
+int dspgn_debug_system(DspgnSolver* s, int obj, int mode, float* H, float* b, float* dx,
+                       float* J_rows, float* res_rows, float* losses /* [sdf, render, V, m] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSPGN_H_ */

@@ -1,0 +1,257 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference
+(/root/reference, PyTorch-CPU, via tools/ref_harness.py) on seeded synthetic inputs.
+
+The reference has no tests or golden vectors of its own, and it cannot travel to
+the GPU box, so these files are what pins the oracle (oracle/dsp_oracle.py) and, through it, the
+CUDA path.  Run in the authoring container only:
+
+    python tools/fit_fixture_decoder.py cars chairs      # once, ~5 min
+    python tests/golden/make_golden.py
+
+Writes stages.npz (single-stage inputs/outputs at a fixed state) and recon_*.npz (whole GN runs,
+with the 71x71 system of every iteration captured by wrapping torch.mv).
+"""
+import os
+import sys
+import json
+import copy
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import ref_harness  # noqa: E402
+from dsp_slam_b200 import synth  # noqa: E402
+
+ns = ref_harness.load()
+torch.set_num_threads(os.cpu_count())
+
+
+def load_ref_decoder(name):
+    d = np.load(os.path.join(HERE, f"decoder_{name}.npz"))
+    spec = json.loads(bytes(d["spec_json"]).decode())
+    dec = ns.decoder.Decoder(**spec)
+    dec.load_state_dict({k: torch.from_numpy(d[k]) for k in d.files if k != "spec_json"})
+    return dec.eval()
+
+
+def cfg_with(name, **joint_overrides):
+    cfg = ref_harness.load_config(name)
+    for k, v in joint_overrides.items():
+        cfg.optimizer.joint_optim[k] = v
+    return cfg
+
+
+class SolveRecorder:
+    """Captures (H, b, dx) of every  dx = mv(inverse(H), b)  the reference performs."""
+
+    def __enter__(self):
+        self.H, self.b, self.dx = [], [], []
+        self._inv, self._mv = torch.inverse, torch.mv
+        rec = self
+
+        def inv(a):
+            r = rec._inv(a)
+            if a.shape[0] > 4:
+                rec.H.append(a.detach().clone().numpy())
+            return r
+
+        def mv(a, b):
+            r = rec._mv(a, b)
+            if a.shape[0] > 4:
+                rec.b.append(b.detach().clone().numpy())
+                rec.dx.append(r.detach().clone().numpy())
+            return r
+
+        torch.inverse, torch.mv = inv, mv
+        return self
+
+    def __exit__(self, *a):
+        torch.inverse, torch.mv = self._inv, self._mv
+
+
+def np_f(x):
+    return np.asfortranarray(np.array(x, dtype=np.float32))
+
+
+def run_reconstruct(dec, cfg, obj, with_code=False):
+    opt = ns.optimizer.Optimizer(dec, cfg)
+    code = None if not with_code else np.array(obj["code_init"], dtype=np.float32)
+    with SolveRecorder() as rec:
+        out = opt.reconstruct_object(np_f(obj["t_cam_obj_init"]), np_f(obj["pts"]),
+                                     np_f(obj["rays"]), np.array(obj["depth"], dtype=np.float32),
+                                     code)
+    res = dict(is_good=np.array(bool(out.is_good)), loss=np.array(float(out.loss), dtype=np.float32))
+    if out.is_good:
+        res["t_cam_obj"] = np.ascontiguousarray(out.t_cam_obj)
+        res["code"] = np.ascontiguousarray(out.code)
+    if rec.H:
+        res["H_iters"] = np.stack(rec.H)
+        res["b_iters"] = np.stack(rec.b)
+        res["dx_iters"] = np.stack(rec.dx)
+    return res
+
+
+def pack_inputs(obj, with_code=False):
+    d = dict(in_t_cam_obj=obj["t_cam_obj_init"], in_pts=obj["pts"], in_rays=obj["rays"],
+             in_depth=obj["depth"], gt_t_cam_obj=obj["t_cam_obj_gt"], gt_code=obj["code_gt"])
+    if with_code:
+        d["in_code"] = obj["code_init"]
+    return d
+
+
+def sdf_only_composed(dec, cfg, obj):
+    """optimizer.py:118-192 with the render block removed, built from the reference's own
+    functions (BASELINE config 2 'surface-SDF loss' mode)."""
+    lu, lo = ns.loss_utils, ns.loss
+    o = cfg.optimizer
+    j = o.joint_optim
+    L = o.code_len
+    z = torch.zeros(L)
+    t_obj_cam = torch.inverse(torch.from_numpy(np.array(obj["t_cam_obj_init"])))
+    pts = torch.from_numpy(np.ascontiguousarray(obj["pts"]))
+    Hs, bs, dxs = [], [], []
+    loss = 0.0
+    for _ in range(j.num_iterations):
+        jt, jc, res = lo.compute_sdf_loss(dec, pts, t_obj_cam, z)
+        rr, sdf_loss, _ = lu.get_robust_res(res, j.b2)
+        drot, res_rot = lo.compute_rotation_loss_sim3(t_obj_cam)
+        loss = j.k2 * sdf_loss
+        J = torch.cat([jt, jc], dim=-1)
+        n = J.shape[0]
+        H = j.k2 * torch.bmm(J.transpose(-2, -1), J).sum(0).squeeze() / n
+        b = -j.k2 * torch.bmm(J.transpose(-2, -1), rr).sum(0).squeeze() / n
+        H[7:7 + L, 7:7 + L] += j.k3 * torch.eye(L)
+        b[7:7 + L] -= j.k3 * z
+        drot = drot.unsqueeze(0)
+        H[:7, :7] += j.k4 * torch.mm(drot.transpose(-2, -1), drot)
+        b[:7] -= j.k4 * (-(drot.transpose(-2, -1) * res_rot).squeeze())
+        H[:7, :7] += torch.eye(7)
+        H[6, 6] += j.scale_damping
+        dx = torch.mv(torch.inverse(H), b)
+        Hs.append(H.clone().numpy()); bs.append(b.clone().numpy()); dxs.append(dx.clone().numpy())
+        t_obj_cam = torch.mm(lu.exp_sim3(j.learning_rate * dx[:7]), t_obj_cam)
+        z = z + j.learning_rate * dx[7:7 + L]
+    return dict(t_cam_obj=torch.inverse(t_obj_cam).numpy(), code=z.numpy(),
+                loss=np.array(float(loss), dtype=np.float32), is_good=np.array(True),
+                H_iters=np.stack(Hs), b_iters=np.stack(bs), dx_iters=np.stack(dxs))
+
+
+def main():
+    cars = load_ref_decoder("cars")
+    chairs = load_ref_decoder("chairs")
+    lu, lo = ns.loss_utils, ns.loss
+    rng = np.random.default_rng(7)
+
+    # ------------------------------------------------------------------ single stages
+    st = {}
+    # folded weights as torch's own weight_norm hook computes them (checked against our fold)
+    with torch.no_grad():
+        cars(torch.zeros(1, 67))
+    for k in range(9):
+        st[f"cars_W{k}"] = getattr(cars, f"lin{k}").weight.detach().numpy().copy()
+    obj = synth.make_object(3, 300, 100, 20)
+    t_oc = torch.inverse(torch.from_numpy(np.array(obj["t_cam_obj_init"])))
+    z = torch.from_numpy((0.05 * rng.standard_normal(64)).astype(np.float32))
+    pts = torch.from_numpy(np.ascontiguousarray(obj["pts"]))
+    x_obj = (pts[..., None, :] * t_oc[:3, :3]).sum(-1) + t_oc[:3, 3]
+    inp = torch.cat([z.expand(x_obj.shape[0], -1), x_obj], 1)
+    with torch.no_grad():
+        st["dec_in"] = inp.numpy().copy()
+        st["dec_y"] = cars(inp).squeeze(-1).numpy().copy()
+    y, g = lu.get_batch_sdf_jacobian(cars, z, x_obj, 1)
+    st["jac_y"] = y.reshape(-1).numpy().copy()
+    st["jac_g"] = g.reshape(-1, 67).numpy().copy()
+    jt, jc, res = lo.compute_sdf_loss(cars, pts, t_oc, z)
+    st["sdf_t_obj_cam"] = t_oc.numpy().copy()
+    st["sdf_z"] = z.numpy().copy()
+    st["sdf_pts"] = pts.numpy().copy()
+    st["sdf_J"] = torch.cat([jt, jc], -1).reshape(-1, 71).numpy().copy()
+    st["sdf_res"] = res.reshape(-1).numpy().copy()
+    # render term at the same state
+    t_co = torch.inverse(t_oc)
+    scale = torch.det(t_co[:3, :3]) ** (1 / 3)
+    dmin, dmax = t_co[2, 3] - scale, t_co[2, 3] + scale
+    depths = torch.linspace(dmin, dmax, 50)
+    rays = torch.from_numpy(np.ascontiguousarray(obj["rays"]))
+    dobs = torch.cat([torch.from_numpy(np.array(obj["depth"])), torch.full((20,), float(1.1 * dmax))])
+    dobs[100:] = 1.1 * dmax
+    rr = lo.compute_render_loss(cars, rays, dobs, t_oc, depths, z, th=0.01)
+    st["rnd_rays"] = rays.numpy().copy()
+    st["rnd_depth_obs"] = dobs.numpy().copy()
+    st["rnd_depths"] = depths.numpy().copy()
+    st["rnd_J"] = torch.cat([rr[0], rr[1]], -1).reshape(-1, 71).numpy().copy()
+    st["rnd_res"] = rr[2].reshape(-1).numpy().copy()
+    # rotation prior: upright-ish initial pose and a 3 degree tilt about x
+    a = np.deg2rad(3.0)
+    Rx = np.array([[1, 0, 0, 0], [0, np.cos(a), -np.sin(a), 0], [0, np.sin(a), np.cos(a), 0],
+                   [0, 0, 0, 1]], dtype=np.float32)
+    for nm, T in (("up", t_oc), ("tilt", torch.inverse(torch.from_numpy(Rx) @ torch.inverse(t_oc)))):
+        Jr, rrot = lo.compute_rotation_loss_sim3(T.clone())
+        st[f"rot_{nm}_T"] = T.numpy().copy()
+        st[f"rot_{nm}_J"] = Jr.numpy().copy()
+        st[f"rot_{nm}_r"] = np.array(float(rrot), dtype=np.float32)
+    # exponential maps
+    xs = np.array([[0.1, -0.2, 0.05, 0.02, -0.03, 0.04, 0.01],
+                   [0.1, -0.2, 0.05, 0.02, -0.03, 0.04, -0.02],
+                   [0.3, 0.1, -0.1, 0, 0, 0, 0.05],
+                   [0.3, 0.1, -0.1, 0, 0, 0, 0.0],
+                   [0, 0, 0, 0, 0, 0, 0],
+                   [-0.5, 0.2, 0.7, 0.4, -0.6, 0.3, 0.0]], dtype=np.float32)
+    st["exp_x"] = xs
+    st["exp_sim3"] = np.stack([lu.exp_sim3(torch.from_numpy(x)).numpy() for x in xs])
+    st["exp_se3"] = np.stack([lu.exp_se3(torch.from_numpy(x[:6])).numpy() for x in xs])
+    # Huber
+    r = torch.from_numpy(np.concatenate([rng.standard_normal(50) * 0.05, [0.0, 0.025, -0.025]]).astype(np.float32))
+    rb, ls, w = lu.get_robust_res(r.clone(), 0.025)
+    st["hub_r"] = r.numpy().copy()
+    st["hub_rr"] = rb.reshape(-1).numpy().copy()
+    st["hub_loss"] = np.array(float(ls), dtype=np.float32)
+    st["lin_ab"] = np.array([float(dmin), float(dmax)], dtype=np.float32)
+    st["lin_out"] = depths.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "stages.npz"), **st)
+    print("stages.npz:", {k: v.shape for k, v in st.items() if k.startswith(("sdf_J", "rnd_J"))})
+
+    # ------------------------------------------------------------------ whole runs
+    # config 1: 1 car, 500 pts, 700 rays, 5 iterations
+    cfg1 = cfg_with("config_kitti.json", num_iterations=5)
+    o = synth.make_object(0, 500, 500, 200)
+    np.savez_compressed(os.path.join(HERE, "recon_cfg1.npz"), **pack_inputs(o),
+                        **run_reconstruct(cars, cfg1, o))
+    # KITTI-like real shape: 250 pts, 450 rays, 10 iterations
+    cfgk = cfg_with("config_kitti.json")
+    o = synth.make_object(1, 250, 250, 200)
+    np.savez_compressed(os.path.join(HERE, "recon_kitti250.npz"), **pack_inputs(o),
+                        **run_reconstruct(cars, cfgk, o))
+    # config 3 shape: chairs, 256 pts, 64+18 rays, initial code, 10 iterations, redwood params
+    cfg3 = cfg_with("config_redwood_01053.json", num_iterations=10)
+    o = synth.make_object(2, 256, 64, 18, cls="chairs", init_code_frac=0.5)
+    np.savez_compressed(os.path.join(HERE, "recon_cfg3.npz"), **pack_inputs(o, True),
+                        **run_reconstruct(chairs, cfg3, o, with_code=True))
+    # sdf_only composition, 512 pts, 10 iterations
+    o = synth.make_object(4, 512, 0, 0)
+    o["rays"] = np.zeros((0, 3), np.float32); o["depth"] = np.zeros((0,), np.float32)
+    np.savez_compressed(os.path.join(HERE, "recon_sdf_only.npz"), **pack_inputs(o),
+                        **sdf_only_composed(cars, cfgk, o))
+    # failure: rays that never enter the unit sphere -> V < 10 -> is_good False
+    o = synth.make_object(5, 200, 50, 10)
+    o["rays"] = np.asfortranarray((o["rays"] * np.array([[-1, -1, 1]], dtype=np.float32) + np.array([[3, 3, 0]], dtype=np.float32)).astype(np.float32))
+    np.savez_compressed(os.path.join(HERE, "recon_fail_few.npz"), **pack_inputs(o),
+                        **run_reconstruct(cars, cfgk, o))
+    # pose-only GN (estimate_pose_cam_obj), 250 pts, 5 iterations
+    o = synth.make_object(6, 250, 0, 0)
+    T = np.array(o["t_cam_obj_init"], dtype=np.float32)
+    s = float(np.cbrt(np.linalg.det(T[:3, :3].astype(np.float64))))
+    se3 = T.copy(); se3[:3, :3] /= s
+    code = (0.8 * o["code_gt"]).astype(np.float32)
+    opt = ns.optimizer.Optimizer(cars, cfgk)
+    Tout = opt.estimate_pose_cam_obj(se3.copy(), s, np_f(o["pts"]), code.copy())
+    np.savez_compressed(os.path.join(HERE, "pose_only.npz"), in_t_co_se3=se3, in_scale=np.array(s, dtype=np.float32),
+                        in_pts=o["pts"], in_code=code, t_cam_obj=Tout.numpy())
+    print("done")
+
+
+if __name__ == "__main__":
+    main()
