@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched per-object shape-prior GN reconstruction.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2_sdf|cfg2_full|cfg3] [--engine auto|simt|tc]
+  python bench.py --impl reference ...      # the CPU restatement of the reference on the host cores
+
+A "step" = one batched call that runs ALL GN iterations for the per-GPU batch (BASELINE config 2 by
+default: 32 objects x 2048 surface points x 10 iterations, surface-SDF loss).  Under torchrun every rank
+owns its own 32 objects (weak scaling) and the solved (pose, code, loss, status) records are all-gathered
+with NCCL inside the step.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_FWD = 918_016          # FLOP / row forward   (459,008 MAC)
+F_BWD = 918_016          # FLOP / row backward-to-input
+F_JTJ = 5_254            # FLOP / row J^T J + J^T r
+
+WORKLOADS = {
+    # name: (objects/GPU, pts, fg rays, bg rays, class, config, sdf_only, description)
+    "cfg2_sdf": (32, 2048, 0, 0, "cars", "config_kitti.json", True,
+                 "BASELINE configs[1]: 32 objects x 2048 surface pts x 10 GN iters, surface-SDF loss"),
+    "cfg2_full": (32, 2048, 2048, 200, "cars", "config_kitti.json", False,
+                  "config 2 full: 32 objects x 2048 pts + 2248 rays x 50 depth samples x 10 GN iters"),
+    "cfg3": (8, 256, 64, 18, "chairs", "config_redwood_01053.json", False,
+             "BASELINE configs[2]: 8 chairs x 256 pts + 82 rays x 50 samples x 10 iters, initial code"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2_sdf", choices=list(WORKLOADS))
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--cpu-sample", type=int, default=4, help="objects in the CPU baseline sample")
+    return ap.parse_args()
+
+
+def make_inputs(workload, rank):
+    from dsp_slam_b200 import synth, load_config
+    B, M, nfg, nbg, cls, cfgname, sdf_only, _ = WORKLOADS[workload]
+    cfg = load_config(cfgname)
+    cfg["optimizer"]["joint_optim"]["num_iterations"] = 10
+    objs = synth.make_batch(B, M, nfg if not sdf_only else 0, nbg if not sdf_only else 0, cls=cls,
+                            seed0=1000 * rank, init_code_frac=0.5 if workload == "cfg3" else None)
+    ins = []
+    for o in objs:
+        d = dict(t_cam_obj=o["t_cam_obj_init"], pts=o["pts"])
+        if not sdf_only:
+            d.update(rays=o["rays"], depth=o["depth"])
+        if o.get("code_init") is not None:
+            d["code"] = o["code_init"]
+        ins.append(d)
+    return cfg, ins, cls, sdf_only
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(gpu_index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, line in self.rows:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                if t0 - 0.05 <= t <= t1 + 0.15:
+                    sm.append(float(p[0]))
+                smax = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active") and t0 - 0.05 <= t <= t1 + 0.15:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(workload, n_sample, steps=1, warmup=0):
+    """The numpy restatement of the reference (oracle/dsp_oracle.py) on the host cores: objects one per
+    call in a Python loop, exactly how the reference batches (src/LocalMapping_util.cc:165-203)."""
+    from oracle import dsp_oracle as O
+    cfg, ins, cls, sdf_only = make_inputs(workload, 0)
+    dw = O.DecoderWeights.from_npz(os.path.join(ROOT, "tests", "golden", f"decoder_{cls}.npz"))
+    ocfg = O.GNConfig.from_json_dict(cfg)
+    sample = ins[:n_sample]
+
+    def one_pass():
+        for o in sample:
+            O.reconstruct_object(dw, ocfg, o["t_cam_obj"], o["pts"], o.get("rays"), o.get("depth"),
+                                 code=o.get("code"), sdf_only=sdf_only)
+    # always one untimed object first: BLAS thread pool spin-up / page-in are not the steady state
+    o = sample[0]
+    O.reconstruct_object(dw, ocfg, o["t_cam_obj"], o["pts"], o.get("rays"), o.get("depth"), code=o.get("code"), sdf_only=sdf_only)
+    # give the CPU leg its best thread count: these GEMMs are small (2048x256x256) and OpenBLAS with one
+    # thread per core of a 100+-core host is slower than with 8-32 threads
+    global _CPU_THREADS
+    try:
+        from threadpoolctl import threadpool_limits
+        x = np.concatenate([np.zeros((o["pts"].shape[0], 64), np.float32), np.asarray(o["pts"], np.float32)], 1)
+        best, cands = None, sorted({t for t in (4, 8, 16, 32, 64, os.cpu_count()) if t <= os.cpu_count()})
+        for t in cands:
+            with threadpool_limits(limits=t):
+                O.decoder_value_and_input_grad(dw, x)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    O.decoder_value_and_input_grad(dw, x)
+                dt = time.perf_counter() - t0
+            if best is None or dt < best[1]:
+                best = (t, dt)
+        _CPU_THREADS = best[0]
+        threadpool_limits(limits=_CPU_THREADS)
+    except Exception:
+        _CPU_THREADS = os.cpu_count()
+    for _ in range(warmup):
+        one_pass()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_pass()
+    dt = (time.perf_counter() - t0) / steps
+    return len(sample) / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, M, nfg, nbg, cls, cfgname, sdf_only, desc = WORKLOADS[args.workload]
+    steps = max(1, min(args.steps, 5))
+    val, dt = cpu_baseline(args.workload, args.cpu_sample, steps=steps, warmup=min(args.warmup, 1))
+    cores = os.cpu_count()
+    out = {
+        "impl": "reference", "metric": "object-recons/sec (2048 pts, 10 GN iters)", "value": val, "unit": "objects/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "objects_per_step": args.cpu_sample},
+        "cpu_baseline": {"value": val, "unit": "objects/s", "cores": _CPU_THREADS or cores, "kind": "port",
+                         "sample": f"{args.cpu_sample} of the {B} objects per step, numpy/OpenBLAS fp32 restatement "
+                                   f"(oracle/dsp_oracle.py), one object per call like the reference"},
+        "e2e": {"value": val, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+_CPU_THREADS = None
+
+
+class _CudaArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    g.build()
+    from dsp_slam_b200.optimizer import Optimizer
+    from dsp_slam_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, M, nfg, nbg, cls, cfgname, sdf_only, desc = WORKLOADS[args.workload]
+    cfg, ins, cls, sdf_only = make_inputs(args.workload, rank)
+    dec = os.path.join(ROOT, "tests", "golden", f"decoder_{cls}.npz")
+    opt = Optimizer(dec, cfg, device=local, engine=None if args.engine == "auto" else args.engine, sdf_only=sdf_only)
+    solver = opt.solver
+    stream = torch.cuda.current_stream()
+    solver.set_stream(stream.cuda_stream)
+    engine = {1: "simt-fp32", 2: "tcgen05-3xf16"}[solver.engine]
+
+    solver.upload(ins)                      # batch resident in HBM before the timed region
+    res_view = torch.as_tensor(_CudaArray(solver.results_device_ptr(), B * _lib.RESULT_FLOATS), device=f"cuda:{local}")
+    gathered = torch.empty(world * B * _lib.RESULT_FLOATS, device=f"cuda:{local}") if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+
+    def step():
+        solver.run(0)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, res_view)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.perf_counter()
+    for a, b in ev:
+        flush.fill_(1)                      # L2 flush (256 MiB write) outside the event pair
+        a.record(stream)
+        step()
+        b.record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    launches_per_step = solver.counters()["kernel_launches"]
+    t = torch.tensor([ms], device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B / (ms * 1e-3)
+
+    # correctness of what was timed: every object converged to a finite, good result
+    out = solver.results_raw()
+    n_good = sum(1 for i in range(B) if out[i].status == 0)
+
+    # ---- end to end through the public call, host buffers, H2D + D2H inside the timed region ------
+    for _ in range(2):
+        opt.reconstruct_batch(ins)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    te = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = opt.reconstruct_batch(ins)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - te) / e2e_steps * 1e3
+    te_t = torch.tensor([e2e_ms], device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te_t.item())
+    h2d = sum(o["pts"].nbytes + 64 + 256 + 40 + (o["rays"].nbytes + o["depth"].nbytes if "rays" in o else 0) for o in ins)
+    d2h = B * 4 * _lib.RESULT_FLOATS
+
+    # ---- roofline of the dominant kernel (decoder fwd+bwd+JtJ over the SDF rows), live CUDA events ---
+    solver.enable_timing(True)
+    dec_ms, n_l = [], 0
+    for _ in range(3):
+        solver.run(0)
+        solver.results_raw()
+        c = solver.counters()
+        dec_ms.append(c["decoder_ms"])
+    solver.enable_timing(False)
+    c = solver.counters()
+    iters = 10
+    n_dec_launch = iters * (1 if sdf_only else 3)
+    rows_fb, rows_f = c["rows_fwd_bwd"], c["rows_fwd_only"]
+    flop_alg = rows_fb * (F_FWD + F_BWD + F_JTJ) + rows_f * F_FWD
+    dec_ms_med = float(np.median(dec_ms))
+    achieved = flop_alg / (dec_ms_med * 1e-3) / 1e12
+    peaks, peak_src = None, "fallback (B200_PROFILING.md)"
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = 1590.0
+    if os.path.isfile(pk):
+        peaks = json.load(open(pk))
+        peak = float(peaks.get("bf16_tflops", peak))
+        peak_src = "MEASURED_PEAKS.json bf16_tflops (burst; decoder launches are ~ms)"
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tp):
+        traffic = json.load(open(tp)).get(f"{args.workload}:{engine}")
+
+    if rank == 0:
+        cpu_val, cpu_dt = cpu_baseline(args.workload, args.cpu_sample)
+        out = {
+            "metric": "object-recons/sec (2048 pts, 10 GN iters)", "value": value, "unit": "objects/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if solver.engine == 1 else "f16x3-split (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": desc, "objects_per_gpu": B, "points": M, "gn_iterations": 10,
+                       "engine": engine, "parallelism": f"object-sharded x{world}, NCCL all-gather of results",
+                       "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
+                       "decoder": "DeepSDF 8x256, L=64, latent_in=[4] (fitted fixture weights)",
+                       "good_objects": f"{n_good}/{B}"},
+            "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "objects/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "decoder fwd+bwd+JtJ (" + engine + ")",
+                         "alg_flop_per_run": flop_alg, "decoder_ms_per_run": dec_ms_med,
+                         "decoder_launches_per_run": n_dec_launch},
+            "cpu_baseline": {"value": cpu_val, "unit": "objects/s", "cores": _CPU_THREADS or os.cpu_count(), "kind": "port",
+                             "sample": f"{args.cpu_sample} of the {B} objects, numpy/OpenBLAS fp32 restatement of the "
+                                       f"reference (oracle/dsp_oracle.py), one object per call"},
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
