@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <new>
+#include <algorithm>
 
 #include "dspgn_common.cuh"
 #include "dspgn_simt.cuh"
@@ -555,6 +556,26 @@ int dspgn_debug_system(DspgnSolver* s, int obj, int mode, float* H, float* b, fl
   dJ.release();
   if (rc) return rc;
   if (e != cudaSuccess) return fail(DSPGN_E_CUDA, std::string("debug_system: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int dspgn_tc_selftest(int device, int n_mma, int k_steps, const float* A, const float* B, float* D) {
+  // D[128][n_mma] = A[128][16*k_steps] * B[n_mma][16*k_steps]^T through the tensor-core operand paths
+  if (!A || !B || !D || n_mma < 16 || n_mma > 256 || (n_mma % 16) || k_steps < 1 || k_steps > 16) return fail(DSPGN_E_ARG, "bad selftest shape");
+  CU(cudaSetDevice(device));
+  if (int rc = tc_setup_kernels(g_err)) return rc;
+  const int K = 16 * k_steps;
+  std::vector<unsigned char> blob;
+  tc_pack_images(blob, n_mma, k_steps, [&](int n, int kk) { return B[(size_t)n * K + kk]; });
+  DevBuf dA, dB, dD;
+  if (dA.reserve(4 * (size_t)128 * K) || dB.reserve(blob.size()) || dD.reserve(4 * (size_t)128 * n_mma)) return fail(DSPGN_E_ALLOC, "cudaMalloc");
+  CU(cudaMemcpy(dA.p, A, 4 * (size_t)128 * K, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dB.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  k_tc_selftest<<<1, 128, 2 * kTcStageBytes + 1024>>>(dA.as<float>(), K, dB.as<unsigned char>(), n_mma, k_steps, dD.as<float>());
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(D, dD.p, 4 * (size_t)128 * n_mma, cudaMemcpyDeviceToHost);
+  dA.release(); dB.release(); dD.release();
+  if (e != cudaSuccess) return fail(DSPGN_E_CUDA, std::string("tc_selftest: ") + cudaGetErrorString(e));
   return 0;
 }
 

@@ -38,6 +38,26 @@ struct ObjState {
   int n_active;                // pose-only inlier count (optimizer.py:76-78)
 };
 
+// ---- tcgen05 engine plan (dspgn_tc.cuh): one entry per GEMM step of a tile -----------------------
+constexpr int kTcMaxSteps = 18;
+enum { TK_FWD_HIDDEN = 0, TK_FWD_LAST = 1, TK_BWD_MID = 2, TK_BWD_FIRST = 3 };
+struct TcStep {
+  int kind;
+  int n_mma;         // UMMA N (multiple of 16, <= 256)
+  int k_steps;       // K=16 steps of the reduction
+  int a_reg, d_reg;  // TMEM region (0/1 -> column 0/256) of the A operand and of the accumulator
+  unsigned w_off;    // byte offset of this step's first weight image in the blob
+  int layer;         // decoder layer (bias / ReLU-mask slot)
+  int n_real;        // real output columns (the rest is zero padding)
+  int cat_off;       // fwd: K index of the NEXT operand where the decoder input is concatenated; bwd: first
+                     // column of the latent_in skip path; -1 = none
+  int mask_layer;    // bwd: ReLU mask applied to the outputs; -1 = none
+};
+struct TcPlan {
+  int n_steps, n_fwd;
+  TcStep step[kTcMaxSteps];
+};
+
 struct SolverParams {
   float k1, k2, k3, k4, b1, b2, lr, s_damp;
   int code_len, D;

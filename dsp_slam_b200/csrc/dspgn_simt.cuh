@@ -22,8 +22,9 @@ struct DecoderDev {
   const float* Wb[DSPGN_MAX_LINEAR];       // backward, reduction-major [out_pad16][256]: Wb[i*256+j] = W[i][j]
   const float* bias[DSPGN_MAX_LINEAR];     // [256] zero padded
   const float* w_last;                     // [256] last layer row
-  // tcgen05 engine images (dspgn_tc.cuh)
-  const void* tc_blob;
+  // tcgen05 engine images (dspgn_tc.cuh): pre-swizzled fp16 hi/lo weight chunks + step plan
+  const unsigned char* tc_blob;
+  TcPlan tc_plan;
 };
 
 enum { MODE_SDF = 0, MODE_BAND = 1, MODE_RAYFWD = 2, MODE_PTSFWD = 3 };

@@ -227,3 +227,22 @@ def test_engines_agree_single_step(dec_path, cfg_kitti):
     assert np.abs(ga["res"] - gb["res"]).max() < 2e-5          # needs >= 15 mantissa bits
     assert rel(gb["J"], ga["J"]) < 2e-4
     assert rel(gb["H"], ga["H"]) < 3e-4 and rel(gb["b"], ga["b"]) < 3e-4
+
+
+@pytest.mark.parametrize("n_mma,k_steps", [(256, 16), (192, 16), (256, 5), (80, 16), (16, 16), (256, 12)])
+def test_tc_operand_paths_selftest(n_mma, k_steps):
+    """tcgen05 plumbing in isolation: D = A B^T with A through the TMEM split-fp16 path and B through the
+    pre-swizzled shared-memory images, vs float64 on the host.  3-pass split => ~1e-6 relative."""
+    import ctypes as C
+    from dsp_slam_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n_mma * 100 + k_steps)
+    K = 16 * k_steps
+    A = rng.standard_normal((128, K)).astype(np.float32)
+    B = (rng.standard_normal((n_mma, K)) * 0.1).astype(np.float32)
+    D = np.zeros((128, n_mma), np.float32)
+    FP = C.POINTER(C.c_float)
+    _lib.check(lib.dspgn_tc_selftest(0, n_mma, k_steps, A.ctypes.data_as(FP), B.ctypes.data_as(FP), D.ctypes.data_as(FP)))
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    err = np.abs(D - ref).max() / np.abs(ref).max()
+    assert err < 5e-6, err
