@@ -89,9 +89,11 @@ struct DspgnSolver {
   DevBuf d_stage;        // one contiguous upload: meta | T_init | code_init | pts | rays | depth
   ObjMeta* d_meta = nullptr; float* d_Tinit = nullptr; float* d_code = nullptr;
   float* d_pts = nullptr; float* d_rays = nullptr; float* d_depth = nullptr;
-  DevBuf d_state, d_acc, d_V, d_m, d_results, d_active;
+  DevBuf d_state, d_part_s, d_part_r, d_tbase, d_V, d_m, d_results, d_active;
   DevBuf d_sdf, d_bx, d_bs, d_br;
   DevBuf d_dbg;
+  DevBuf d_clk;
+  bool clk_on = false;
   HostBuf h_results;
   // counters
   DspgnCounters ctr{};
@@ -231,6 +233,12 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
   s->engine = eng;
   CU(cudaFuncSetAttribute(k_decoder_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimtSmem)));
   if (int rc = tc_setup_kernels(g_err)) { delete s; return rc; }
+  if (getenv("DSPGN_CLK")) {
+    const size_t nb = sizeof(long long) * kClkTiles * kTcMaxSteps * kClkSlots;
+    if (s->d_clk.reserve(nb)) { delete s; return fail(DSPGN_E_ALLOC, "cudaMalloc"); }
+    CU(cudaMemset(s->d_clk.p, 0, nb));
+    s->clk_on = true;
+  }
   CU(cudaEventCreate(&s->ev_run0));
   CU(cudaEventCreate(&s->ev_run1));
   *out = s;
@@ -241,8 +249,8 @@ void dspgn_solver_destroy(DspgnSolver* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&s->d_decs, &s->d_stage, &s->d_state, &s->d_acc, &s->d_V, &s->d_m, &s->d_results, &s->d_active,
-                    &s->d_sdf, &s->d_bx, &s->d_bs, &s->d_br, &s->d_dbg}) b->release();
+  for (DevBuf* b : {&s->d_decs, &s->d_stage, &s->d_state, &s->d_part_s, &s->d_part_r, &s->d_tbase, &s->d_V, &s->d_m, &s->d_results, &s->d_active,
+                    &s->d_sdf, &s->d_bx, &s->d_bs, &s->d_br, &s->d_dbg, &s->d_clk}) b->release();
   s->h_stage.release();
   s->h_results.release();
   for (auto e : s->ev) cudaEventDestroy(e);
@@ -330,7 +338,13 @@ int dspgn_upload_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in) {
   s->n_obj = n_obj; s->tot_pts = (int)tp; s->tot_rays = (int)tr; s->tot_fg = (int)tf; s->tot_smp = ts; s->max_rays = max_rays;
   int bad = 0;
   bad |= s->d_state.reserve(sizeof(ObjState) * n_obj);
-  bad |= s->d_acc.reserve(sizeof(double) * 2 * kAccStride * (size_t)n_obj);
+  {
+    // per-tile partial sums: one slot per possible tile of each term (rows/tile of the smaller-tile engine)
+    const size_t tiles_s = (size_t)tp / kTP + n_obj + 1, tiles_r = (size_t)ts / kTP + n_obj + 1;
+    bad |= s->d_part_s.reserve(4 * (size_t)kAccStride * tiles_s);
+    if (!s->cfg.sdf_only) bad |= s->d_part_r.reserve(4 * (size_t)kAccStride * tiles_r);
+    bad |= s->d_tbase.reserve(4 * 2 * (size_t)n_obj);
+  }
   bad |= s->d_V.reserve(4 * (size_t)n_obj);
   bad |= s->d_m.reserve(4 * (size_t)n_obj);
   bad |= s->d_results.reserve(4 * DSPGN_RESULT_FLOATS * (size_t)n_obj);
@@ -375,19 +389,22 @@ int launch_term(DspgnSolver* s, TermArgs& a, long long rows_upper) {
 TermArgs base_term(DspgnSolver* s, int mode) {
   TermArgs a{};
   a.meta = s->d_meta; a.state = s->d_state.as<ObjState>(); a.decs = s->d_decs.as<DecoderDev>();
-  a.n_obj = s->n_obj; a.mode = mode;
+  a.n_obj = s->n_obj; a.n_classes = (int)s->classes.size(); a.mode = mode;
   a.pts = s->d_pts; a.pt_active = nullptr; a.rays = s->d_rays;
   a.band_x = s->d_bx.as<float>(); a.band_s = s->d_bs.as<float>(); a.band_r = s->d_br.as<float>();
   a.band_m = s->d_m.as<int>(); a.sdf_out = s->d_sdf.as<float>(); a.V_count = s->d_V.as<int>();
-  a.acc = s->d_acc.as<double>(); a.D = s->cfg.num_depth_samples;
+  a.part = (mode == MODE_BAND) ? s->d_part_r.as<float>() : (mode == MODE_SDF ? s->d_part_s.as<float>() : nullptr);
+  a.tile_base = (mode == MODE_BAND) ? s->d_tbase.as<int>() + s->n_obj : (mode == MODE_SDF ? s->d_tbase.as<int>() : nullptr);
+  a.D = s->cfg.num_depth_samples;
   a.dbg_J = nullptr; a.dbg_res = nullptr; a.dbg_obj = -1; a.dbg_P = 0;
+  a.dbg_clk = (s->clk_on && mode == MODE_SDF) ? s->d_clk.as<long long>() : nullptr;
   return a;
 }
 
 int launch_init(DspgnSolver* s, int pose_only) {
   InitArgs ia{};
   ia.meta = s->d_meta; ia.state = s->d_state.as<ObjState>(); ia.T_init = s->d_Tinit; ia.code_init = s->d_code;
-  ia.acc = s->d_acc.as<double>(); ia.V_count = s->d_V.as<int>(); ia.band_m = s->d_m.as<int>();
+  ia.V_count = s->d_V.as<int>(); ia.band_m = s->d_m.as<int>();
   ia.pt_active = nullptr; ia.n_obj = s->n_obj; ia.code_len = s->cfg.code_len; ia.D = s->cfg.num_depth_samples;
   ia.pose_only = pose_only;
   k_init<<<s->n_obj, 128, 0, s->stream>>>(ia);
@@ -429,7 +446,10 @@ int launch_terms(DspgnSolver* s, int pose_only, float* dbg_J, float* dbg_res, in
 SolveArgs base_solve(DspgnSolver* s, int pose_only) {
   const DspgnConfig& c = s->cfg;
   SolveArgs v{};
-  v.meta = s->d_meta; v.state = s->d_state.as<ObjState>(); v.acc = s->d_acc.as<double>();
+  v.meta = s->d_meta; v.state = s->d_state.as<ObjState>();
+  v.part_s = s->d_part_s.as<float>(); v.part_r = s->d_part_r.as<float>();
+  v.base_s = s->d_tbase.as<int>(); v.base_r = s->d_tbase.as<int>() + s->n_obj;
+  v.tile_rows = (s->engine == DSPGN_ENGINE_TC) ? kTcRows : kTP;
   v.V_count = s->d_V.as<int>(); v.band_m = s->d_m.as<int>();
   v.prm = SolverParams{c.k1, c.k2, c.k3, c.k4, c.b1, c.b2, c.lr, c.s_damp, c.code_len, c.num_depth_samples, c.cut_off, c.sdf_only};
   v.n_obj = s->n_obj; v.pose_only = pose_only; v.results = s->d_results.as<float>();
@@ -556,6 +576,17 @@ int dspgn_debug_system(DspgnSolver* s, int obj, int mode, float* H, float* b, fl
   dJ.release();
   if (rc) return rc;
   if (e != cudaSuccess) return fail(DSPGN_E_CUDA, std::string("debug_system: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int dspgn_debug_clocks(DspgnSolver* s, long long* out, int n) {
+  // phase timeline of CTA 0's first tiles of the last SDF-term launch (enabled by env DSPGN_CLK=1 at solver creation)
+  if (!s || !out) return fail(DSPGN_E_ARG, "null argument");
+  if (!s->clk_on) return fail(DSPGN_E_ARG, "timeline not enabled (DSPGN_CLK)");
+  const int have = kClkTiles * kTcMaxSteps * kClkSlots;
+  CU(cudaSetDevice(s->device));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaMemcpy(out, s->d_clk.p, sizeof(long long) * (size_t)std::min(n, have), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -10,7 +10,7 @@ namespace dspgn {
 
 constexpr int kMaxCode = DSPGN_MAX_CODE;       // 64
 constexpr int kPInt = 72;                      // internal Jacobian row stride: [code 0..63 | pose 64..70 | pad]
-constexpr int kAccStride = kPInt * kPInt + kPInt + 8;  // doubles per (object, term): H | b | {loss_sum, rows, ...}
+constexpr int kAccStride = kPInt * kPInt + kPInt + 8;  // floats per tile partial: H (upper) | b | {loss_sum, rows, ...}
 constexpr int kAccB = kPInt * kPInt;
 constexpr int kAccLoss = kAccB + kPInt;        // +0 loss sum, +1 row count (double)
 constexpr int kTermSdf = 0, kTermRender = 1;

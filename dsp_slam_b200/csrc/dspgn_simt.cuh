@@ -34,6 +34,7 @@ struct TermArgs {
   ObjState* state;
   const DecoderDev* decs;
   int n_obj;
+  int n_classes;
   int mode;
   // sources
   const float* pts;          // MODE_SDF: camera-frame points (xyz interleaved)
@@ -45,12 +46,14 @@ struct TermArgs {
   const int* band_m;         // rows per object
   float* sdf_out;            // MODE_RAYFWD: per sample sdf (+inf when outside the unit sphere)
   int* V_count;              // MODE_RAYFWD: valid samples per object
-  double* acc;               // [n_obj][2][kAccStride]
+  float* part;               // per-tile partial sums of this term: [tile][kAccStride] (H upper | b | loss, rows)
+  int* tile_base;            // [n_obj] first tile of each object in this launch (written by CTA 0)
   float huber_b;
   int D;
   int pose_only;             // 1: 6-D se3 Jacobian (no scale column)
   // debug dump of Jacobian rows (external order [pose | code]) for one object
   float* dbg_J; float* dbg_res; int dbg_obj; int dbg_P;
+  long long* dbg_clk;         // optional phase timeline of CTA 0 (tensor-core engine)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -84,6 +87,8 @@ __device__ inline int build_tile_prefix(const TermArgs& a, int tile_rows, int* s
   }
   if (tid == 0) s_prefix[a.n_obj] = carry;
   __syncthreads();
+  if (blockIdx.x == 0 && a.tile_base != nullptr)
+    for (int o = tid; o < a.n_obj; o += blockDim.x) a.tile_base[o] = s_prefix[o];
   return carry;
 }
 
@@ -345,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decoder_simt(TermArgs a) {
       if (tid < nrows) a.dbg_res[row0 + tid] = S.yv[tid];
     }
     // ---- phase 4: H += J^T J, b += J^T (rho r), loss += sum (rho r)^2  (optimizer.py:161-167) ----
-    double* accp = a.acc + ((size_t)o * 2 + (a.mode == MODE_BAND ? kTermRender : kTermSdf)) * kAccStride;
+    float* accp = a.part + (size_t)tile * kAccStride;
     if (tid < 171) {
       // upper-triangular 4x4 blocks of the 72x72 matrix: tid -> (bi <= bj)
       int bi = 0, rem = tid;
@@ -376,22 +381,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_decoder_simt(TermArgs a) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           const int r = 4 * bi + u, c = 4 * bj + v;
-          if (c >= r && c < kMaxCode + 7) atomic_add_f64(accp + r * kPInt + c, (double)h[u][v]);
+          if (c >= r && c < kMaxCode + 7) accp[r * kPInt + c] = h[u][v];
         }
     } else if (tid < 171 + kMaxCode + 7) {
       const int c = tid - 171;
       const float* rj = S.act + c * kTP;
       float s = 0.f;
       for (int p = 0; p < kTP; ++p) s = fmaf(rj[p], S.rr[p], s);
-      atomic_add_f64(accp + kAccB + c, (double)s);
+      accp[kAccB + c] = s;
     } else if (tid == 255) {
       float s = 0.f, n = 0.f;
       for (int p = 0; p < kTP; ++p) {
         s = fmaf(S.rr[p], S.rr[p], s);
         n += (a.mode == MODE_SDF) ? S.rscale[p] : (p < nrows ? 1.f : 0.f);
       }
-      atomic_add_f64(accp + kAccLoss, (double)s);
-      atomic_add_f64(accp + kAccLoss + 1, (double)n);
+      accp[kAccLoss] = s;
+      accp[kAccLoss + 1] = n;
     }
     __syncthreads();
   }

@@ -11,7 +11,6 @@ struct InitArgs {
   ObjState* state;
   const float* T_init;     // [n_obj][16] row-major object->camera
   const float* code_init;  // [n_obj][64]
-  double* acc;             // zeroed here
   int* V_count;
   int* band_m;
   uint8_t* pt_active;      // [total_pts] reset to 1 (pose-only mode)
@@ -22,8 +21,6 @@ __global__ void k_init(InitArgs a) {
   const int o = blockIdx.x, tid = threadIdx.x;
   ObjState& st = a.state[o];
   const ObjMeta M = a.meta[o];
-  double* acc = a.acc + (size_t)o * 2 * kAccStride;
-  for (int i = tid; i < 2 * kAccStride; i += blockDim.x) acc[i] = 0.0;
   if (a.pt_active != nullptr)
     for (int i = tid; i < M.n_pts; i += blockDim.x) a.pt_active[M.pts_off + i] = 1;
   if (tid < kMaxCode) st.z[tid] = (M.has_code && tid < a.code_len) ? a.code_init[o * kMaxCode + tid] : 0.f;
@@ -46,7 +43,11 @@ __global__ void k_init(InitArgs a) {
 struct SolveArgs {
   const ObjMeta* meta;
   ObjState* state;
-  double* acc;
+  const float* part_s;     // SDF-term tile partials [tile][kAccStride]
+  const float* part_r;     // render-term (band rows) tile partials
+  const int* base_s;       // [n_obj] first tile of each object in the SDF / band launches
+  const int* base_r;
+  int tile_rows;           // rows per tile of the decoder engine
   int* V_count;
   int* band_m;
   SolverParams prm;
@@ -59,8 +60,10 @@ struct SolveArgs {
   int dbg_obj; float* dbg_H; float* dbg_b; float* dbg_dx; float* dbg_loss;
 };
 
-constexpr int kSolveThreads = 128;
+constexpr int kSolveThreads = 256;
 constexpr int kPMax = 7 + kMaxCode;   // 71
+constexpr int kHsStride = kPMax + 1;  // row stride of the factorisation workspace (doubles)
+constexpr int kMaxEnt = (kPMax * (kPMax + 1) / 2 + kPMax + kSolveThreads - 1) / kSolveThreads;   // 11
 
 __device__ __forceinline__ int ext_to_int(int e, int npose, int L) {
   // external order [pose | code]  ->  internal rows [code 0..63 | pose 64..70]
@@ -87,10 +90,14 @@ __device__ void write_result(const SolveArgs& a, int o, const ObjState& st) {
   reinterpret_cast<int*>(r)[85] = 0;
 }
 
+// One CTA per object.  The normal system H dx = b (optimizer.py:161-186) is assembled in fp64 from the
+// fp64 accumulators and solved by an LDL^T factorisation in shared memory.  b rides along as row P of
+// the lower triangle, so after the factorisation that row holds the forward-substituted vector; each
+// thread owns a fixed set of <= 11 lower-triangle entries, one barrier per pivot.
 __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
-  __shared__ double Hs[kPMax * kPMax];
-  __shared__ double bs[kPMax];
-  __shared__ double dxs[kPMax];
+  __shared__ double Hs[(kPMax + 1) * kHsStride];
+  __shared__ double xs[kPMax];
+  __shared__ float s_rot[4];       // J_rot.x, J_rot.z, res_rot, active
   __shared__ int s_flag;
   const int o = blockIdx.x, tid = threadIdx.x;
   ObjState& st = a.state[o];
@@ -98,26 +105,31 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
   const int L = prm.code_len;
   const int npose = a.pose_only ? 6 : 7;
   const int P = a.pose_only ? 6 : (7 + L);
-  double* accS = a.acc + ((size_t)o * 2 + kTermSdf) * kAccStride;
-  double* accR = a.acc + ((size_t)o * 2 + kTermRender) * kAccStride;
   const bool dbg = (a.dbg_H != nullptr);
+  const bool use_render = !a.pose_only && !prm.sdf_only;
+  // tile partials of this object, summed in tile order (deterministic), fp64
+  const int V = a.V_count[o], m = use_render ? a.band_m[o] : 0;
+  const int ntS = (a.meta[o].n_pts + a.tile_rows - 1) / a.tile_rows;
+  const int ntR = use_render ? (m + a.tile_rows - 1) / a.tile_rows : 0;
+  const float* pS = a.part_s + (size_t)a.base_s[o] * kAccStride;
+  const float* pR = use_render ? a.part_r + (size_t)a.base_r[o] * kAccStride : nullptr;
+  auto sumS = [&](int idx) { double v = 0.0; for (int t = 0; t < ntS; ++t) v += (double)pS[(size_t)t * kAccStride + idx]; return v; };
+  auto sumR = [&](int idx) { double v = 0.0; for (int t = 0; t < ntR; ++t) v += (double)pR[(size_t)t * kAccStride + idx]; return v; };
 
+  // ---- losses and the reference's soft-failure exits (optimizer.py:130-150) -----------------
   if (st.status != 0) {                          // frozen object: keep its record
     if (a.last_iter && tid == 0 && !dbg) write_result(a, o, st);
     return;
   }
-  // ---- losses and the reference's soft-failure exits (optimizer.py:130-150) -----------------
-  const double nS = accS[kAccLoss + 1];
-  const float sdf_loss = (float)(accS[kAccLoss] / nS);
-  const int V = a.V_count[o], m = a.band_m[o];
+  const double nS = sumS(kAccLoss + 1);
+  const float sdf_loss = (float)(sumS(kAccLoss) / nS);
   float render_loss = 0.f;
   int status = 0;
-  const bool use_render = !a.pose_only && !prm.sdf_only;
   if (isnan(sdf_loss)) status = DSPGN_ST_SDF_NAN;
   else if (use_render) {
     if (V < 10) status = DSPGN_ST_RENDER_FEW;
     else {
-      render_loss = (m > 0) ? (float)(accR[kAccLoss] / (double)m) : NAN;
+      render_loss = (m > 0) ? (float)(sumR(kAccLoss) / (double)m) : NAN;
       if (isnan(render_loss)) status = DSPGN_ST_RENDER_NAN;
     }
   }
@@ -125,40 +137,15 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
     a.dbg_loss[0] = sdf_loss; a.dbg_loss[1] = render_loss; a.dbg_loss[2] = (float)V; a.dbg_loss[3] = (float)m;
   }
   if (status != 0) {
-    __syncthreads();
-    if (!dbg) {
-      if (tid == 0) { st.status = status; st.V = V; st.m = m; if (a.last_iter) write_result(a, o, st); }
-    }
+    if (!dbg && tid == 0) { st.status = status; st.V = V; st.m = m; if (a.last_iter) write_result(a, o, st); }
     return;
   }
   const float loss = prm.k1 * render_loss + prm.k2 * sdf_loss;     // optimizer.py:155
 
-  // ---- assemble H, b (optimizer.py:161-184; pose-only: optimizer.py:68-71) ------------------
-  const double wS = a.pose_only ? 1.0 / nS : (double)prm.k2 / nS;
-  const double wR = use_render ? (double)prm.k1 / (double)m : 0.0;
-  for (int idx = tid; idx < P * P; idx += kSolveThreads) {
-    const int r = idx / P, c = idx - r * P;
-    int ri = ext_to_int(r, npose, L), ci = ext_to_int(c, npose, L);
-    if (ri > ci) { int t = ri; ri = ci; ci = t; }          // accumulators hold the upper triangle
-    double h = wS * accS[ri * kPInt + ci];
-    if (use_render) h += wR * accR[ri * kPInt + ci];
-    Hs[idx] = h;
-  }
-  for (int r = tid; r < P; r += kSolveThreads) {
-    const int ri = ext_to_int(r, npose, L);
-    double v = -wS * accS[kAccB + ri];
-    if (use_render) v -= wR * accR[kAccB + ri];
-    bs[r] = v;
-  }
-  __syncthreads();
-  if (a.pose_only) {
-    if (tid < 6) Hs[tid * P + tid] += 1e-2;                              // optimizer.py:70
-  } else {
-    if (tid < L) {                                                       // optimizer.py:170-172
-      Hs[(7 + tid) * P + 7 + tid] += (double)prm.k3;
-      bs[7 + tid] -= (double)prm.k3 * (double)st.z[tid];
-    }
-    if (tid == 0) {
+  if (tid == 0) {
+    s_flag = 0;
+    s_rot[0] = s_rot[1] = s_rot[2] = s_rot[3] = 0.f;
+    if (!a.pose_only) {
       // rotation prior (loss.py:155-178): r = 1 - (R_co e_y).n_g, n_g = (0,-1,0)
       float Tco[12];
       double det_oc;
@@ -172,82 +159,109 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
       const float res_rot = 1.0f + rco[1 * 4 + 1];                     // 1 - dot(R_co[:,1], (0,-1,0))
       if (!(res_rot < 1e-7f)) {
         // v = R_oc n_g = -R_oc[:,1];  J_rot = v x e_y = (-v_z, 0, v_x)
-        const float vx = -roc[0 * 4 + 1], vz = -roc[2 * 4 + 1];
-        const double J[3] = {(double)(-vz), 0.0, (double)vx};
-        for (int u = 0; u < 3; ++u) {
-          for (int v = 0; v < 3; ++v) Hs[(3 + u) * P + 3 + v] += (double)prm.k4 * J[u] * J[v];
-          bs[3 + u] += (double)prm.k4 * J[u] * (double)res_rot;      // optimizer.py:177-179 sign
-        }
+        s_rot[0] = roc[2 * 4 + 1];      // -v_z
+        s_rot[1] = -roc[0 * 4 + 1];     //  v_x
+        s_rot[2] = res_rot;
+        s_rot[3] = 1.f;
       }
-      for (int u = 0; u < 7; ++u) Hs[u * P + u] += 1.0;               // optimizer.py:182
-      Hs[6 * P + 6] += (double)prm.s_damp;                            // optimizer.py:183
     }
-  }
-  __syncthreads();
-  if (dbg && o == a.dbg_obj) {
-    for (int idx = tid; idx < P * P; idx += kSolveThreads) a.dbg_H[idx] = (float)Hs[idx];
-    for (int r = tid; r < P; r += kSolveThreads) a.dbg_b[r] = (float)bs[r];
   }
   __syncthreads();
 
-  // ---- Cholesky H = L L^T in fp64, in place (lower triangle), then two triangular solves --------
-  if (tid == 0) s_flag = 0;
+  // ---- assemble the lower triangle of H and the b row (optimizer.py:161-184; pose-only: :68-71) ----
+  const double wS = a.pose_only ? 1.0 / nS : (double)prm.k2 / nS;
+  const double wR = use_render ? (double)prm.k1 / (double)m : 0.0;
+  const int nTri = P * (P + 1) / 2, nEnt = nTri + P;
+  int ei[kMaxEnt], ej[kMaxEnt];
+#pragma unroll
+  for (int q = 0; q < kMaxEnt; ++q) {
+    const int e = tid + q * kSolveThreads;
+    int i = -1, j = 0;
+    if (e < nTri) {
+      i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+      while ((i + 1) * (i + 2) / 2 <= e) ++i;
+      while (i * (i + 1) / 2 > e) --i;
+      j = e - i * (i + 1) / 2;
+    } else if (e < nEnt) {
+      i = P; j = e - nTri;
+    }
+    ei[q] = i; ej[q] = j;
+    if (i < 0) continue;
+    double v;
+    if (i < P) {
+      int ri = ext_to_int(i, npose, L), ci = ext_to_int(j, npose, L);
+      if (ri > ci) { int t = ri; ri = ci; ci = t; }        // accumulators hold the upper triangle
+      v = wS * sumS(ri * kPInt + ci);
+      if (use_render) v += wR * sumR(ri * kPInt + ci);
+      if (a.pose_only) {
+        if (i == j) v += 1e-2;                                           // optimizer.py:70
+      } else {
+        if (i == j && i >= 7) v += (double)prm.k3;                       // optimizer.py:170
+        if (i == j && i < 7) v += 1.0;                                   // optimizer.py:182
+        if (i == 6 && j == 6) v += (double)prm.s_damp;                   // optimizer.py:183
+        if (s_rot[3] != 0.f && i >= 3 && i < 6 && j >= 3) {              // optimizer.py:176-178
+          const double Ji = (i == 3) ? s_rot[0] : (i == 5 ? s_rot[1] : 0.0);
+          const double Jj = (j == 3) ? s_rot[0] : (j == 5 ? s_rot[1] : 0.0);
+          v += (double)prm.k4 * Ji * Jj;
+        }
+      }
+      if (dbg && o == a.dbg_obj) { a.dbg_H[i * P + j] = (float)v; a.dbg_H[j * P + i] = (float)v; }
+    } else {
+      const int ri = ext_to_int(j, npose, L);
+      v = -wS * sumS(kAccB + ri);
+      if (use_render) v -= wR * sumR(kAccB + ri);
+      if (!a.pose_only) {
+        if (j >= 7) v -= (double)prm.k3 * (double)st.z[j - 7];           // optimizer.py:172
+        if (s_rot[3] != 0.f && (j == 3 || j == 5))                       // optimizer.py:177-179 sign
+          v += (double)prm.k4 * (double)(j == 3 ? s_rot[0] : s_rot[1]) * (double)s_rot[2];
+      }
+      if (dbg && o == a.dbg_obj) a.dbg_b[j] = (float)v;
+    }
+    Hs[i * kHsStride + j] = v;
+  }
   __syncthreads();
+
+  // ---- LDL^T: for pivot k, every entry (i,j) with j > k loses H[i][k] H[j][k] / d_k ------------------
   for (int k = 0; k < P; ++k) {
-    if (tid == 0) {
-      const double d = Hs[k * P + k];
-      if (!(d > 0.0) || !isfinite(d)) { s_flag = 1; Hs[k * P + k] = 1.0; }
-      else Hs[k * P + k] = sqrt(d);
+    const double d = Hs[k * kHsStride + k];
+    if (!(d > 0.0) || !isfinite(d)) { if (tid == 0) s_flag = 1; break; }    // uniform: all threads read the same d
+    const double inv = 1.0 / d;
+#pragma unroll
+    for (int q = 0; q < kMaxEnt; ++q) {
+      const int i = ei[q], j = ej[q];
+      if (i >= 0 && j > k) Hs[i * kHsStride + j] -= Hs[i * kHsStride + k] * Hs[j * kHsStride + k] * inv;
     }
     __syncthreads();
-    const double inv = 1.0 / Hs[k * P + k];
-    for (int i = k + 1 + tid; i < P; i += kSolveThreads) Hs[i * P + k] *= inv;
-    __syncthreads();
-    const int n = P - k - 1;
-    for (int idx = tid; idx < n * n; idx += kSolveThreads) {
-      const int i = k + 1 + idx / n, j = k + 1 + idx % n;
-      if (j <= i) Hs[i * P + j] -= Hs[i * P + k] * Hs[j * P + k];
-    }
-    __syncthreads();
-  }
-  if (tid < 32) {
-    // forward  L y = b, backward  L^T x = y  (one warp; dot products split over lanes)
-    const int lane = tid;
-    for (int i = 0; i < P; ++i) {
-      double s = 0.0;
-      for (int j = lane; j < i; j += 32) s += Hs[i * P + j] * dxs[j];
-      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-      if (lane == 0) dxs[i] = (bs[i] - s) / Hs[i * P + i];
-      __syncwarp();
-    }
-    for (int i = P - 1; i >= 0; --i) {
-      double s = 0.0;
-      for (int j = i + 1 + lane; j < P; j += 32) s += Hs[j * P + i] * dxs[j];
-      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-      if (lane == 0) dxs[i] = (dxs[i] - s) / Hs[i * P + i];
-      __syncwarp();
-    }
   }
   __syncthreads();
-  if (tid == 0) {
-    for (int i = 0; i < P; ++i) if (!isfinite(dxs[i])) s_flag = 1;
+  // ---- back substitution  L^T x = D^-1 w  (w = row P), column oriented -------------------------------
+  const bool bad = (s_flag != 0);
+  if (!bad) {
+    if (tid < P) xs[tid] = Hs[P * kHsStride + tid] / Hs[tid * kHsStride + tid];
+    __syncthreads();
+    for (int i = P - 1; i > 0; --i) {
+      const double xi = xs[i];
+      if (tid < i) xs[tid] -= (Hs[i * kHsStride + tid] / Hs[tid * kHsStride + tid]) * xi;
+      __syncthreads();
+    }
+    if (tid < P && !isfinite(xs[tid])) s_flag = 1;
+    __syncthreads();
   }
-  __syncthreads();
   if (dbg) {
-    if (o == a.dbg_obj) for (int r = tid; r < P; r += kSolveThreads) a.dbg_dx[r] = (float)dxs[r];
+    if (o == a.dbg_obj && tid < P) a.dbg_dx[tid] = (float)xs[tid];
     return;
   }
   // ---- update (optimizer.py:186-192 / :72-74), clear accumulators, next depth range -----------
-  for (int i = tid; i < 2 * kAccStride; i += kSolveThreads) a.acc[(size_t)o * 2 * kAccStride + i] = 0.0;
-  if (!a.pose_only && tid < L && !s_flag) st.z[tid] += prm.lr * (float)dxs[tid + 7];
+  const bool fail = (s_flag != 0);
+  if (!a.pose_only && tid < L && !fail) st.z[tid] += prm.lr * (float)xs[tid + 7];
   if (tid == 0) {
     st.loss = loss; st.V = V; st.m = m;
     a.V_count[o] = 0;
-    if (s_flag) {
+    if (fail) {
       st.status = DSPGN_ST_SOLVE;
     } else {
       float dp[7];
-      for (int i = 0; i < npose; ++i) dp[i] = (a.pose_only ? 1.0f : prm.lr) * (float)dxs[i];
+      for (int i = 0; i < npose; ++i) dp[i] = (a.pose_only ? 1.0f : prm.lr) * (float)xs[i];
       float dT[12], Tn[12];
       exp_sim3_dev(dp, !a.pose_only, dT);
       mul_affine(dT, st.T_oc, Tn);

@@ -90,6 +90,25 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
       "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// whole-warp variants: called converged by all 32 lanes, one elected lane issues.  Keeping the control flow
+// warp-uniform lets the compiler hold descriptors in uniform registers instead of R2UR moves per operand.
+__device__ __forceinline__ void tc_mma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -134,6 +153,14 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32])
       : "memory");
 }
 
+// debug timeline (CTA 0 only, when TermArgs.dbg_clk != nullptr): [tile][step][slot] = clock64
+constexpr int kClkSlots = 8, kClkTiles = 4;
+#define DSPGN_CLK(slot)                                                                                   \
+  do {                                                                                                    \
+    if (a.dbg_clk != nullptr && blockIdx.x == 0 && clk_tile < kClkTiles)                                  \
+      a.dbg_clk[((size_t)clk_tile * kTcMaxSteps + s) * kClkSlots + (slot)] = clock64();                   \
+  } while (0)
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
@@ -165,42 +192,72 @@ __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint3
 // ------------------------------------------------------------------------------------------------
 // shared-memory carve-up
 // ------------------------------------------------------------------------------------------------
+constexpr int kJpStride = 76;             // floats per row of the point-major Jacobian tile (72 + pad, 16B aligned)
 struct TcSmemTail {
-  float Jt[kPInt * kTcRows];              // [72][128] Jacobian rows (feature-major); rows 0..66 double as skip grad
-  uint32_t maskw[8 * 8 * kTcRows];        // ReLU masks [layer][word][row]
+  float Jp[kTcRows * kJpStride];          // [row][72+4]: J row of each point; cols 0..66 double as latent_in skip gradient
+  uint32_t maskw[8 * 8 * kTcRows];        // ReLU masks [layer][32-col word][row]
   float bias[9 * kHid];
   float wlast[kHid];
-  float zs[kMaxCode];
+  float zs[kMaxCode + 16];                // latent code of the tile's object (zero padded)
+  float xr[3 * kTcRows];                  // object-frame point of every row
   float rr[kTcRows], rsc[kTcRows];
   int prefix[kMaxObjScan + 1];
   int warp_tmp[32];
   uint64_t w_full[kTcStages], w_empty[kTcStages];
-  uint64_t acc_full, a_ready;
+  uint64_t acc_full[4];                   // accumulator quarter q (64 columns) of the current step is complete
+  uint64_t a_ready[8];                    // 32-column unit u of the next A operand has been written
   uint32_t tmem_base;
   int cur_class;
+  TcPlan plans[DSPGN_MAX_CLASSES];        // step plans of every decoder class (read by all warp roles)
 };
 constexpr size_t kTcSmemBytes = 1024 + (size_t)kTcStages * kTcStageBytes + sizeof(TcSmemTail);
 
-// one 64-column block of the NEXT A operand from 64 fp32 values: hi -> cols [0,32), lo -> cols [32,64)
-__device__ __forceinline__ void store_a_block(uint32_t taddr, const float (&t)[64]) {
-  uint32_t hi[32], lo[32];
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      DSPGN_W8(v, 0), DSPGN_W8(v, 8)
+      : "memory");
+}
+
+// A-operand layout inside a 256-column TMEM region: 32-column units, unit u holds K elements [32u, 32u+32):
+// fp16 "hi" halves packed in columns [32u, 32u+16), "lo" halves in [32u+16, 32u+32).
+// K-step t (16 elements) -> hi at column 32*(t>>1) + 8*(t&1), lo 16 columns further.
+__device__ __forceinline__ uint32_t a_col_hi(int t) { return (uint32_t)(32 * (t >> 1) + 8 * (t & 1)); }
+
+__device__ __forceinline__ void store_a_unit(uint32_t taddr, const float (&t)[32]) {
+  uint32_t hi[16], lo[16];
 #pragma unroll
-  for (int p = 0; p < 32; ++p) split_pack(t[2 * p], t[2 * p + 1], hi[p], lo[p]);
-  tc_st32(taddr, hi);
-  tc_st32(taddr + 32, lo);
+  for (int p = 0; p < 16; ++p) split_pack(t[2 * p], t[2 * p + 1], hi[p], lo[p]);
+  tc_st16(taddr, hi);
+  tc_st16(taddr + 16, lo);
+}
+
+// signal "unit u of the next A operand is in TMEM" (or simply "done with this unit")
+__device__ __forceinline__ void unit_done(uint64_t* bar) {
+  tc_wait_st();
+  tc_fence_before();
+  mbar_arrive(bar);
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
   extern __shared__ unsigned char tc_smem_raw[];
-  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* ring = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   TcSmemTail& S = *reinterpret_cast<TcSmemTail*>(ring + (size_t)kTcStages * kTcStageBytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int total_tiles = build_tile_prefix(a, kTcRows, S.prefix, S.warp_tmp);
+  {
+    const int nwords = a.n_classes * (int)(sizeof(TcPlan) / 4);
+    for (int i = tid; i < nwords; i += kTcThreads) {
+      const int c = i / (int)(sizeof(TcPlan) / 4), w = i % (int)(sizeof(TcPlan) / 4);
+      reinterpret_cast<int*>(&S.plans[c])[w] = reinterpret_cast<const int*>(&a.decs[c].tc_plan)[w];
+    }
+  }
   if (tid == 0) {
     for (int i = 0; i < kTcStages; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
-    mbar_init(&S.acc_full, 1);
-    mbar_init(&S.a_ready, kTcEpiThreads);
+    mbar_init(&S.acc_full[0], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&S.a_ready[i], 128);
     S.cur_class = -1;
     fence_barrier_init();
   }
@@ -217,13 +274,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int o = find_object(S.prefix, a.n_obj, tile);
-        const DecoderDev& dec = a.decs[a.meta[o].class_id];
-        const int ns = fwd_only ? dec.tc_plan.n_fwd : dec.tc_plan.n_steps;
+        const int cls = a.meta[o].class_id;
+        const TcPlan& plan = S.plans[cls];
+        const unsigned char* blob = a.decs[cls].tc_blob;
+        const int ns = fwd_only ? plan.n_fwd : plan.n_steps;
         for (int s = 0; s < ns; ++s) {
-          const TcStep& st = dec.tc_plan.step[s];
+          const TcStep st = plan.step[s];
           const uint32_t img = (uint32_t)st.n_mma * 128u;
           const int nch = (st.k_steps + 3) >> 2;
-          const unsigned char* src = dec.tc_blob + st.w_off;
+          const unsigned char* src = blob + st.w_off;
           for (int c = 0; c < 2 * nch; ++c) {           // hi image, lo image, hi, lo, ...
             mbar_wait(&S.w_empty[stage], phase ^ 1);
             mbar_expect_tx(&S.w_full[stage], img);
@@ -235,75 +294,89 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
     }
   } else if (warp == 8) {
     // ===================== MMA issuer ===========================================================
+    // Full-width MMAs (N = the layer's padded output width): with the A operand in TMEM an MMA costs >= ~110
+    // cycles whatever its N (measured), so N is never split.  Overlap with the epilogue comes from the
+    // per-unit a_ready barriers: K chunk c of a step only needs operand units 2c and 2c+1.
     uint32_t stage = 0, phase = 0, ar_phase = 0;
+    int clk_tile = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      ++clk_tile;
       const int o = find_object(S.prefix, a.n_obj, tile);
-      const DecoderDev& dec = a.decs[a.meta[o].class_id];
-      const int ns = fwd_only ? dec.tc_plan.n_fwd : dec.tc_plan.n_steps;
+      const TcPlan& plan = S.plans[a.meta[o].class_id];
+      const int ns = fwd_only ? plan.n_fwd : plan.n_steps;
       for (int s = 0; s < ns; ++s) {
-        const TcStep& st = dec.tc_plan.step[s];
-        mbar_wait(&S.a_ready, ar_phase);
-        ar_phase ^= 1;
-        tc_fence_after();
-        const uint32_t idesc = make_idesc(st.n_mma);
+        const TcStep st = plan.step[s];
         const uint32_t d_t = tmem + (uint32_t)st.d_reg * 256u;
         const uint32_t a_t = tmem + (uint32_t)st.a_reg * 256u;
         const int nch = (st.k_steps + 3) >> 2;
+        const uint32_t idesc = make_idesc(st.n_mma);
         for (int c = 0; c < nch; ++c) {
-          const int nq = min(4, st.k_steps - 4 * c);
-          const uint32_t a_blk = a_t + (uint32_t)c * 64u;     // hi at +8q, lo at +32+8q
+          const int nk = min(4, st.k_steps - 4 * c);
+          const bool last = (c == nch - 1);
+          // both 32-column units of this chunk must have been written by the epilogue warps; before the
+          // LAST chunk (whose commit releases the accumulator) every unit of the previous step must be
+          // finished, so no barrier phase can run ahead of a slow epilogue group
+          mbar_wait(&S.a_ready[2 * c], ar_phase);
+          mbar_wait(&S.a_ready[2 * c + 1], ar_phase);
+          if (last)
+            for (int u = 2 * c + 2; u < 8; ++u) mbar_wait(&S.a_ready[u], ar_phase);
+          if (c == 0 && lane == 0) DSPGN_CLK(4);
           // ---- W_hi image: A_hi*W_hi + A_lo*W_hi
           mbar_wait(&S.w_full[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
+          {
             const uint32_t b0 = smem_u32(ring + (size_t)stage * kTcStageBytes);
-            for (int q = 0; q < nq; ++q) {
-              const uint64_t bd = make_b_desc(b0 + 32u * q);
-              tc_mma_ts(d_t, a_blk + 8u * q, bd, idesc, (c | q) ? 1u : 0u);
-              tc_mma_ts(d_t, a_blk + 32u + 8u * q, bd, idesc, 1u);
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t bd = make_b_desc(b0 + 32u * k);
+              const uint32_t ah = a_t + 64u * c + a_col_hi(k);
+              tc_mma_ts_elect(d_t, ah, bd, idesc, (c | k) ? 1u : 0u);
+              tc_mma_ts_elect(d_t, ah + 16u, bd, idesc, 1u);
             }
-            tc_commit(&S.w_empty[stage]);
+            tc_commit_elect(&S.w_empty[stage]);
           }
-          __syncwarp();
           if (++stage == kTcStages) { stage = 0; phase ^= 1; }
           // ---- W_lo image: A_hi*W_lo
           mbar_wait(&S.w_full[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
+          {
             const uint32_t b0 = smem_u32(ring + (size_t)stage * kTcStageBytes);
-            for (int q = 0; q < nq; ++q) tc_mma_ts(d_t, a_blk + 8u * q, make_b_desc(b0 + 32u * q), idesc, 1u);
-            tc_commit(&S.w_empty[stage]);
-            if (c == nch - 1) tc_commit(&S.acc_full);
+            for (int k = 0; k < nk; ++k) tc_mma_ts_elect(d_t, a_t + 64u * c + a_col_hi(k), make_b_desc(b0 + 32u * k), idesc, 1u);
+            tc_commit_elect(&S.w_empty[stage]);
+            if (last) { tc_commit_elect(&S.acc_full[0]); if (lane == 0) DSPGN_CLK(5); }
           }
-          __syncwarp();
           if (++stage == kTcStages) { stage = 0; phase ^= 1; }
         }
+        ar_phase ^= 1;
       }
     }
   } else {
     // ===================== epilogue groups ======================================================
-    const int grp = warp >> 2;                       // column half owned by this group
-    const int r = tid & 127;                         // tile row == TMEM lane
+    // group g (warps 4g..4g+3) converts operand units g, g+2, g+4, g+6 (32 columns each), in that order, so
+    // that the two units of K chunk c are produced concurrently by the two groups; thread = tile row = TMEM lane.
+    const int grp = warp >> 2;
+    const int r = tid & 127;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t acc_phase = 0;
+    int clk_tile = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      ++clk_tile;
       const int o = find_object(S.prefix, a.n_obj, tile);
       const int row0 = (tile - S.prefix[o]) * kTcRows;
       const ObjMeta M = a.meta[o];
       const ObjState& ost = a.state[o];
       const DecoderDev& dec = a.decs[M.class_id];
-      const TcPlan& plan = dec.tc_plan;
-      const int L = dec.L, in0 = dec.in0;
+      const TcPlan& plan = S.plans[M.class_id];
+      const int L = dec.L, in0 = dec.in0, n_lin = dec.n_lin;
+      const bool has_skip = dec.latent_in >= 0;
       const int nrows = min(kTcRows, term_rows(a, o) - row0);
       const int ns = fwd_only ? plan.n_fwd : plan.n_steps;
 
-      // ---- per-class constants in smem (bias, last row) and the tile's latent code -----------------
+      // ---- per-class constants in smem (bias, last row), the tile's latent code, this row's point ----
       if (S.cur_class != M.class_id) {
-        for (int i = tid; i < dec.n_lin * kHid; i += kTcEpiThreads) S.bias[i] = dec.bias[i / kHid][i % kHid];
+        for (int i = tid; i < n_lin * kHid; i += kTcEpiThreads) S.bias[i] = dec.bias[i / kHid][i % kHid];
         for (int i = tid; i < kHid; i += kTcEpiThreads) S.wlast[i] = dec.w_last[i];
       }
-      if (tid < kMaxCode) S.zs[tid] = (tid < L) ? ost.z[tid] : 0.f;
-      // ---- this row's point in the object frame --------------------------------------------------
+      if (tid < kMaxCode + 16) S.zs[tid] = (tid < L) ? ost.z[tid] : 0.f;
       float x0 = 0.f, x1 = 0.f, x2 = 0.f, sc = 0.f, res_in = 0.f;
       if (r < nrows) {
         const int rr_ = row0 + r;
@@ -323,76 +396,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
           sc = (sqrtf(x0 * x0 + x1 * x1 + x2 * x2) < 1.0f) ? 1.f : 0.f;
         }
       }
-      epi_bar_sync();                                // zs / bias visible; previous tile fully drained
+      if (grp == 0) { S.xr[r] = x0; S.xr[kTcRows + r] = x1; S.xr[2 * kTcRows + r] = x2; }
+      epi_bar_sync();                                // zs / xr / bias visible; previous tile fully drained
       if (tid == 0) S.cur_class = M.class_id;
 
-      // decoder input element i of this row: [z | x]
-      auto inp = [&](int i) -> float { return (i < L) ? S.zs[i] : (i == L ? x0 : (i == L + 1 ? x1 : (i == L + 2 ? x2 : 0.f))); };
+      // decoder input element i of this row: [z | x | 0...]
+      auto inp = [&](int i) -> float {
+        const int j = i - L;
+        return (j < 0) ? S.zs[i] : ((unsigned)j < 3u ? S.xr[j * kTcRows + r] : 0.f);
+      };
 
       // ---- A operand of step 0: the decoder input, K padded to k_steps*16 ---------------------------
       {
-        const TcStep& s0 = plan.step[0];
+        const TcStep s0 = plan.step[0];
         const uint32_t a_t = tmem + (uint32_t)s0.a_reg * 256u + lane_addr;
-        const int nblk = (s0.k_steps + 3) >> 2;
-        for (int blk = 2 * grp; blk < 2 * grp + 2; ++blk) {
-          if (blk >= nblk) break;
-          float t[64];
+        const int kk = s0.k_steps * 16;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const int u = grp + 2 * j, n0 = 32 * u;
+          if (n0 < kk) {
+            float t[32];
 #pragma unroll
-          for (int i = 0; i < 64; ++i) t[i] = inp(blk * 64 + i);
-          store_a_block(a_t + (uint32_t)blk * 64u, t);
+            for (int i = 0; i < 32; ++i) t[i] = inp(n0 + i);
+            store_a_unit(a_t + (uint32_t)n0, t);
+          }
+          unit_done(&S.a_ready[u]);
         }
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(&S.a_ready);
       }
 
       float yv = 0.f;
       for (int s = 0; s < ns; ++s) {
-        const TcStep& st = plan.step[s];
-        mbar_wait(&S.acc_full, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
+        const TcStep st = plan.step[s];
+        const bool more = (s + 1 < ns);
+        const int a_next = more ? plan.step[s + 1].a_reg : 0;
+        const int k_next = more ? plan.step[s + 1].k_steps * 16 : 0;
         const uint32_t d_t = tmem + (uint32_t)st.d_reg * 256u + lane_addr;
+        const uint32_t an_t = tmem + (uint32_t)a_next * 256u + lane_addr;
+        mbar_wait(&S.acc_full[0], acc_phase);
+        tc_fence_after();
+        if (tid == 0) DSPGN_CLK(0);
 
-        if (st.kind == TK_FWD_HIDDEN) {
-          const uint32_t an_t = tmem + (uint32_t)plan.step[s + 1].a_reg * 256u + lane_addr;
-          const int k_next = plan.step[s + 1].k_steps * 16;
-          for (int blk = 2 * grp; blk < 2 * grp + 2; ++blk) {
-            const int n0 = blk * 64;
-            if (n0 >= k_next) break;
-            float t[64];
-            uint32_t m0 = 0, m1 = 0;
-            if (n0 < st.n_mma) {
-              uint32_t v0[32], v1[32];
-              tc_ld32(d_t + (uint32_t)n0, v0);
-              tc_ld32(d_t + (uint32_t)n0 + 32u, v1);
-              tc_wait_ld();
-              const float* bb = S.bias + st.layer * kHid + n0;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float u = __uint_as_float(v0[i]) + bb[i];
-                float w = __uint_as_float(v1[i]) + bb[32 + i];
-                m0 |= (u > 0.f ? 1u : 0u) << i;
-                m1 |= (w > 0.f ? 1u : 0u) << i;
-                t[i] = fmaxf(u, 0.f);
-                t[32 + i] = fmaxf(w, 0.f);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 64; ++i) t[i] = 0.f;
-            }
-            S.maskw[(st.layer * 8 + blk * 2) * kTcRows + r] = m0;
-            S.maskw[(st.layer * 8 + blk * 2 + 1) * kTcRows + r] = m1;
-            if (st.cat_off >= 0 && n0 + 64 > st.cat_off) {      // deep_sdf_decoder.py:87-88: cat[x, input]
-#pragma unroll
-              for (int i = 0; i < 64; ++i) {
-                const int n = n0 + i;
-                if (n >= st.cat_off) t[i] = inp(n - st.cat_off);
-              }
-            }
-            store_a_block(an_t + (uint32_t)n0, t);
-          }
-        } else if (st.kind == TK_FWD_LAST) {
+        if (st.kind == TK_FWD_LAST) {
+          // ---- sdf value; seed of the backward chain (or the forward-only output) ---------------------
           const float d0 = __uint_as_float(tc_ld1(d_t));
           tc_wait_ld();
           yv = tanhf(d0 + S.bias[st.layer * kHid]);                  // deep_sdf_decoder.py:107-108
@@ -405,113 +450,141 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
               const unsigned b = __ballot_sync(0xffffffffu, grp == 0 && r < nrows && sc != 0.f);
               if (lane == 0 && b) atomicAdd(a.V_count + o, __popc(b));
             }
-          } else {
-            // seed of the backward chain: g = (1 - y^2) W_last, masked by the last hidden ReLU
-            const uint32_t an_t = tmem + (uint32_t)plan.step[s + 1].a_reg * 256u + lane_addr;
+          }
+          if (more) {
+            // the next step's MMAs overwrite accumulator column 0: both groups must have read y first
+            epi_bar_sync();
+            // g = (1 - y^2) W_last, masked by the last hidden ReLU   (written into the dead A region of this step)
             const float gy = 1.f - yv * yv;
-            const int ml = st.layer - 1;             // ReLU mask of the last hidden layer
-            for (int blk = 2 * grp; blk < 2 * grp + 2; ++blk) {
-              const int n0 = blk * 64;
-              if (n0 >= plan.step[s + 1].k_steps * 16) break;
-              const uint32_t m0 = S.maskw[(ml * 8 + blk * 2) * kTcRows + r], m1 = S.maskw[(ml * 8 + blk * 2 + 1) * kTcRows + r];
-              float t[64];
+            const int ml = st.layer - 1;
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+              const int u = grp + 2 * j, n0 = 32 * u;
+              if (n0 < k_next) {
+                const uint32_t mw = S.maskw[(ml * 8 + u) * kTcRows + r];
+                float t[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                t[i] = ((m0 >> i) & 1u) ? gy * S.wlast[n0 + i] : 0.f;
-                t[32 + i] = ((m1 >> i) & 1u) ? gy * S.wlast[n0 + 32 + i] : 0.f;
+                for (int i = 0; i < 32; ++i) t[i] = ((mw >> i) & 1u) ? gy * S.wlast[n0 + i] : 0.f;
+                store_a_unit(an_t + (uint32_t)n0, t);
               }
-              store_a_block(an_t + (uint32_t)n0, t);
+              unit_done(&S.a_ready[u]);
             }
+          }
+        } else if (st.kind == TK_FWD_HIDDEN) {
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const int u = grp + 2 * j, n0 = 32 * u;
+            if (n0 < k_next) {
+              float t[32];
+              uint32_t mw = 0;
+              if (n0 < st.n_mma) {
+                uint32_t v[32];
+                tc_ld32(d_t + (uint32_t)n0, v);
+                tc_wait_ld();
+                const float* bb = S.bias + st.layer * kHid + n0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const float w = __uint_as_float(v[i]) + bb[i];
+                  mw |= (w > 0.f ? 1u : 0u) << i;
+                  t[i] = fmaxf(w, 0.f);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) t[i] = 0.f;
+              }
+              S.maskw[(st.layer * 8 + u) * kTcRows + r] = mw;
+              if (st.cat_off >= 0 && n0 + 32 > st.cat_off) {      // deep_sdf_decoder.py:87-88: cat[x, input]
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (n0 + i >= st.cat_off) t[i] = inp(n0 + i - st.cat_off);
+              }
+              store_a_unit(an_t + (uint32_t)n0, t);
+            }
+            unit_done(&S.a_ready[u]);
           }
         } else if (st.kind == TK_BWD_MID) {
-          const uint32_t an_t = tmem + (uint32_t)plan.step[s + 1].a_reg * 256u + lane_addr;
-          const int k_next = plan.step[s + 1].k_steps * 16;
-          for (int blk = 2 * grp; blk < 2 * grp + 2; ++blk) {
-            const int n0 = blk * 64;
-            if (n0 >= st.n_mma) break;
-            uint32_t v0[32], v1[32];
-            tc_ld32(d_t + (uint32_t)n0, v0);
-            tc_ld32(d_t + (uint32_t)n0 + 32u, v1);
-            tc_wait_ld();
-            const uint32_t m0 = S.maskw[(st.mask_layer * 8 + blk * 2) * kTcRows + r];
-            const uint32_t m1 = S.maskw[(st.mask_layer * 8 + blk * 2 + 1) * kTcRows + r];
-            float t[64];
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const int u = grp + 2 * j, n0 = 32 * u;
+            if (n0 < st.n_mma) {
+              uint32_t v[32];
+              tc_ld32(d_t + (uint32_t)n0, v);
+              tc_wait_ld();
+              const uint32_t mw = S.maskw[(st.mask_layer * 8 + u) * kTcRows + r];
+              float t[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              t[i] = ((m0 >> i) & 1u) ? __uint_as_float(v0[i]) : 0.f;
-              t[32 + i] = ((m1 >> i) & 1u) ? __uint_as_float(v1[i]) : 0.f;
-            }
-            if (st.cat_off >= 0 && n0 + 64 > st.cat_off) {      // latent_in skip path -> d/d(input)
+              for (int i = 0; i < 32; ++i) t[i] = ((mw >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
+              if (st.cat_off >= 0 && n0 + 32 > st.cat_off) {      // latent_in skip path -> d/d(input)
 #pragma unroll
-              for (int i = 0; i < 64; ++i) {
-                const int n = n0 + i;
-                if (n >= st.cat_off && n < st.cat_off + in0) {
-                  const int ii = n - st.cat_off;
-                  const int jrow = (ii < L) ? ii : (kMaxCode + ii - L);
-                  S.Jt[jrow * kTcRows + r] = __uint_as_float(i < 32 ? v0[i & 31] : v1[i & 31]);
+                for (int i = 0; i < 32; ++i) {
+                  const int ii = n0 + i - st.cat_off;
+                  if (ii >= 0) {
+                    if (ii < in0) S.Jp[r * kJpStride + ((ii < L) ? ii : (kMaxCode + ii - L))] = __uint_as_float(v[i]);
+                    t[i] = 0.f;
+                  }
                 }
-                if (n >= st.cat_off) t[i] = 0.f;
               }
+              if (n0 < k_next) store_a_unit(an_t + (uint32_t)n0, t);
             }
-            if (n0 < k_next) store_a_block(an_t + (uint32_t)n0, t);
+            unit_done(&S.a_ready[u]);
           }
-        } else {  // TK_BWD_FIRST: d/d(input) complete -> Jacobian row of this point
-          if (grp == 0) {
-            uint32_t v0[32], v1[32];
-            uint32_t v2[16];
-            tc_ld32(d_t, v0);
-            tc_ld32(d_t + 32u, v1);
-            if (st.n_mma > 64) tc_ld16(d_t + 64u, v2);
-            tc_wait_ld();
-            const bool has_skip = dec.latent_in >= 0;
-            float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        } else {
+          // ---- TK_BWD_FIRST: d/d(input) complete -> Jacobian row (loss.py:34-41 / :143-150) -------------
+          float* jr = S.Jp + r * kJpStride;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const int n0 = 32 * (grp + 2 * j);
+            if (n0 < st.n_mma && n0 < in0) {
+              uint32_t v[32];
+              tc_ld32(d_t + (uint32_t)n0, v);         // columns beyond n_mma are never used below
+              tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 80; ++i) {
-              if (i < in0 && i < st.n_mma) {
-                float v = __uint_as_float(i < 32 ? v0[i & 31] : (i < 64 ? v1[i & 31] : v2[i & 15]));
-                const int jrow = (i < L) ? i : (kMaxCode + i - L);
-                if (has_skip) v += S.Jt[jrow * kTcRows + r];
-                v *= sc;                                        // loss.py:145 (de_ds) / inactive rows
-                if (i < L) S.Jt[jrow * kTcRows + r] = v;
-                else if (i == L) g0 = v; else if (i == L + 1) g1 = v; else g2 = v;
+              for (int i = 0; i < 32; ++i) {
+                const int ii = n0 + i;
+                if (ii < in0) {
+                  const int jc = (ii < L) ? ii : (kMaxCode + ii - L);
+                  float g = __uint_as_float(v[i]);
+                  if (has_skip) g += jr[jc];
+                  jr[jc] = g * sc;                                 // loss.py:145 (de_ds) / inactive rows
+                }
               }
             }
-            for (int i = L; i < kMaxCode; ++i) S.Jt[i * kTcRows + r] = 0.f;
-            // dsdf/dx . [I | -x^ | x] = [g, x cross g, g.x]   (loss_utils.py:166-185)
-            S.Jt[(kMaxCode + 0) * kTcRows + r] = g0;
-            S.Jt[(kMaxCode + 1) * kTcRows + r] = g1;
-            S.Jt[(kMaxCode + 2) * kTcRows + r] = g2;
-            S.Jt[(kMaxCode + 3) * kTcRows + r] = x1 * g2 - x2 * g1;
-            S.Jt[(kMaxCode + 4) * kTcRows + r] = x2 * g0 - x0 * g2;
-            S.Jt[(kMaxCode + 5) * kTcRows + r] = x0 * g1 - x1 * g0;
-            S.Jt[(kMaxCode + 6) * kTcRows + r] = a.pose_only ? 0.f : (g0 * x0 + g1 * x1 + g2 * x2);
-            S.Jt[(kMaxCode + 7) * kTcRows + r] = 0.f;
-            float res = (a.mode == MODE_SDF) ? yv : res_in;
-            if (sc == 0.f && (a.mode == MODE_SDF || r >= nrows)) res = 0.f;
-            S.rr[r] = huber_weight(fabsf(res), a.huber_b) * res;
-            S.rsc[r] = (a.mode == MODE_SDF) ? sc : (r < nrows ? 1.f : 0.f);
-            if (a.dbg_J != nullptr && o == a.dbg_obj && a.mode == MODE_SDF && r < nrows) a.dbg_res[row0 + r] = res;
           }
         }
-        if (s + 1 < ns) {
-          tc_wait_st();
-          tc_fence_before();
-          mbar_arrive(&S.a_ready);
-        }
+        if (tid == 0) DSPGN_CLK(3);
+        acc_phase ^= 1;
       }
       if (fwd_only) continue;
 
-      // ---- J^T J, J^T (rho r), loss over the 128 rows of the tile (optimizer.py:161-167) -------------
+      // ---- pose columns, residual (thread = row; needs every d/d(input) column of the row) -----------
+      epi_bar_sync();
+      if (grp == 0) {
+        float* jr = S.Jp + r * kJpStride;
+        for (int i = L; i < kMaxCode; ++i) jr[i] = 0.f;
+        const float g0 = jr[kMaxCode], g1 = jr[kMaxCode + 1], g2 = jr[kMaxCode + 2];
+        // dsdf/dx . [I | -x^ | x] = [g, x cross g, g.x]   (loss_utils.py:166-185)
+        jr[kMaxCode + 3] = x1 * g2 - x2 * g1;
+        jr[kMaxCode + 4] = x2 * g0 - x0 * g2;
+        jr[kMaxCode + 5] = x0 * g1 - x1 * g0;
+        jr[kMaxCode + 6] = a.pose_only ? 0.f : (g0 * x0 + g1 * x1 + g2 * x2);
+        jr[kMaxCode + 7] = 0.f;
+        float res = (a.mode == MODE_SDF) ? yv : res_in;
+        if (sc == 0.f && (a.mode == MODE_SDF || r >= nrows)) res = 0.f;
+        S.rr[r] = huber_weight(fabsf(res), a.huber_b) * res;
+        S.rsc[r] = (a.mode == MODE_SDF) ? sc : (r < nrows ? 1.f : 0.f);
+        if (a.dbg_J != nullptr && o == a.dbg_obj && a.mode == MODE_SDF && r < nrows) a.dbg_res[row0 + r] = res;
+      }
       epi_bar_sync();
       if (a.dbg_J != nullptr && o == a.dbg_obj && a.mode == MODE_SDF) {
         const int P = a.dbg_P, npose = P - L;
         for (int idx = tid; idx < nrows * P; idx += kTcEpiThreads) {
           const int p = idx / P, c = idx - p * P;
           const int ci = (c < npose) ? (kMaxCode + c) : (c - npose);
-          a.dbg_J[(size_t)(row0 + p) * P + c] = S.Jt[ci * kTcRows + p];
+          a.dbg_J[(size_t)(row0 + p) * P + c] = S.Jp[p * kJpStride + ci];
         }
       }
-      double* accp = a.acc + ((size_t)o * 2 + (a.mode == MODE_BAND ? kTermRender : kTermSdf)) * kAccStride;
+      // ---- J^T J, J^T (rho r), loss over the 128 rows of the tile (optimizer.py:161-167) -------------
+      float* accp = a.part + (size_t)tile * kAccStride;
       if (tid < 171) {
         int bi = 0, rem = tid;
         while (rem >= 18 - bi) { rem -= 18 - bi; ++bi; }
@@ -521,41 +594,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
         for (int u = 0; u < 4; ++u)
 #pragma unroll
           for (int v = 0; v < 4; ++v) h[u][v] = 0.f;
-        const float* ra = S.Jt + (4 * bi) * kTcRows;
-        const float* rb = S.Jt + (4 * bj) * kTcRows;
-        for (int p = 0; p < kTcRows; p += 4) {
-          float4 A4[4], B4[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            A4[u] = *reinterpret_cast<const float4*>(ra + u * kTcRows + p);
-            B4[u] = *reinterpret_cast<const float4*>(rb + u * kTcRows + p);
-          }
+        const float* pa = S.Jp + 4 * bi;
+        const float* pb = S.Jp + 4 * bj;
+#pragma unroll 4
+        for (int p = 0; p < kTcRows; ++p) {
+          const float4 A4 = *reinterpret_cast<const float4*>(pa + p * kJpStride);
+          const float4 B4 = *reinterpret_cast<const float4*>(pb + p * kJpStride);
+          const float av[4] = {A4.x, A4.y, A4.z, A4.w}, bv[4] = {B4.x, B4.y, B4.z, B4.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int v = 0; v < 4; ++v)
-              h[u][v] += A4[u].x * B4[v].x + A4[u].y * B4[v].y + A4[u].z * B4[v].z + A4[u].w * B4[v].w;
+            for (int v = 0; v < 4; ++v) h[u][v] = fmaf(av[u], bv[v], h[u][v]);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             const int rI = 4 * bi + u, cI = 4 * bj + v;
-            if (cI >= rI && cI < kMaxCode + 7) atomic_add_f64(accp + rI * kPInt + cI, (double)h[u][v]);
+            if (cI >= rI && cI < kMaxCode + 7) accp[rI * kPInt + cI] = h[u][v];
           }
       } else if (tid < 171 + kMaxCode + 7) {
         const int c = tid - 171;
-        const float* rj = S.Jt + c * kTcRows;
         float sacc = 0.f;
-        for (int p = 0; p < kTcRows; ++p) sacc = fmaf(rj[p], S.rr[p], sacc);
-        atomic_add_f64(accp + kAccB + c, (double)sacc);
-      } else if (tid == 255) {
+        for (int p = 0; p < kTcRows; ++p) sacc = fmaf(S.Jp[p * kJpStride + c], S.rr[p], sacc);
+        accp[kAccB + c] = sacc;
+      } else if (tid >= 248) {
+        // loss and row count: 8 threads x 16 rows, fixed-order combine
+        const int k = tid - 248;
         float sacc = 0.f, n = 0.f;
-        for (int p = 0; p < kTcRows; ++p) { sacc = fmaf(S.rr[p], S.rr[p], sacc); n += S.rsc[p]; }
-        atomic_add_f64(accp + kAccLoss, (double)sacc);
-        atomic_add_f64(accp + kAccLoss + 1, (double)n);
+        for (int p = 16 * k; p < 16 * k + 16; ++p) { sacc = fmaf(S.rr[p], S.rr[p], sacc); n += S.rsc[p]; }
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+          sacc += __shfl_down_sync(0xff000000u, sacc, d);
+          n += __shfl_down_sync(0xff000000u, n, d);
+        }
+        if (k == 0) { accp[kAccLoss] = sacc; accp[kAccLoss + 1] = n; }
       }
-      // next tile's prologue starts with epi_bar_sync(): Jt / rr are not touched before it
+      // the next tile's prologue starts with epi_bar_sync(): Jp / rr are not rewritten before it
     }
   }
   tc_fence_before();
@@ -570,7 +645,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
 __global__ void __launch_bounds__(128, 1) k_tc_selftest(const float* __restrict__ A, int lda, const unsigned char* __restrict__ blob,
                                                         int n_mma, int k_steps, float* __restrict__ D) {
   extern __shared__ unsigned char st_raw[];
-  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(st_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* ring = st_raw + ((1024u - (smem_u32(st_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar_w, bar_acc;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -583,14 +658,14 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const float* __restrict_
   const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
   const int nch = (k_steps + 3) >> 2;
   // A operand -> TMEM region 0
-  for (int blk = 0; blk < nch; ++blk) {
-    float t[64];
+  for (int u = 0; u < 2 * nch; ++u) {
+    float t[32];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) {
-      const int kk = blk * 64 + i;
+    for (int i = 0; i < 32; ++i) {
+      const int kk = u * 32 + i;
       t[i] = (kk < k_steps * 16) ? A[(size_t)tid * lda + kk] : 0.f;
     }
-    store_a_block(tmem + lane_addr + (uint32_t)blk * 64u, t);
+    store_a_unit(tmem + lane_addr + (uint32_t)u * 32u, t);
   }
   tc_wait_st();
   tc_fence_before();
@@ -613,9 +688,9 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const float* __restrict_
       const uint32_t bh = smem_u32(ring), bl = smem_u32(ring + kTcStageBytes);
       const uint32_t a_blk = tmem + (uint32_t)c * 64u;
       for (int q = 0; q < nq; ++q) {
-        tc_mma_ts(tmem + 256u, a_blk + 8u * q, make_b_desc(bh + 32u * q), idesc, (c | q) ? 1u : 0u);
-        tc_mma_ts(tmem + 256u, a_blk + 32u + 8u * q, make_b_desc(bh + 32u * q), idesc, 1u);
-        tc_mma_ts(tmem + 256u, a_blk + 8u * q, make_b_desc(bl + 32u * q), idesc, 1u);
+        tc_mma_ts(tmem + 256u, a_blk + a_col_hi(q), make_b_desc(bh + 32u * q), idesc, (c | q) ? 1u : 0u);
+        tc_mma_ts(tmem + 256u, a_blk + a_col_hi(q) + 16u, make_b_desc(bh + 32u * q), idesc, 1u);
+        tc_mma_ts(tmem + 256u, a_blk + a_col_hi(q), make_b_desc(bl + 32u * q), idesc, 1u);
       }
       tc_commit(&bar_acc);
     }

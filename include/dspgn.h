@@ -163,6 +163,10 @@ int dspgn_enable_timing(DspgnSolver* s, int on);
 int dspgn_debug_system(DspgnSolver* s, int obj, int mode, float* H, float* b, float* dx,
                        float* J_rows, float* res_rows, float* losses /* [sdf, render, V, m] */);
 
+/* Debug: clock64 timeline of CTA 0 of the tensor-core decoder kernel, [4 tiles][18 steps][8 slots]
+ * (only when the solver was created with env DSPGN_CLK set). */
+int dspgn_debug_clocks(DspgnSolver* s, long long* out, int n);
+
 /* Test hook for the tcgen05 operand paths: D[128][n_mma] = A[128][16*k_steps] * B[n_mma][16*k_steps]^T
  * (A through the TMEM split-fp16 path, B through the pre-swizzled shared-memory images). Host buffers. */
 int dspgn_tc_selftest(int device, int n_mma, int k_steps, const float* A, const float* B, float* D);
