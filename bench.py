@@ -278,6 +278,7 @@ def run_ours(args):
         solver.results_raw()
         c = solver.counters()
         dec_ms.append(c["decoder_ms"])
+        solve_ms = c["solve_ms"]; total_ms = c["total_ms"]
     solver.enable_timing(False)
     c = solver.counters()
     iters = 10
@@ -318,6 +319,7 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "decoder fwd+bwd+JtJ (" + engine + ")",
                          "alg_flop_per_run": flop_alg, "decoder_ms_per_run": dec_ms_med,
+                         "solve_ms_per_run": solve_ms, "run_ms_with_event_overhead": total_ms,
                          "decoder_launches_per_run": n_dec_launch},
             "cpu_baseline": {"value": cpu_val, "unit": "objects/s", "cores": _CPU_THREADS or os.cpu_count(), "kind": "port",
                              "sample": f"{args.cpu_sample} of the {B} objects, numpy/OpenBLAS fp32 restatement of the "

@@ -50,7 +50,8 @@ class ObjectOut(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("rows_fwd_bwd", C.c_int64), ("rows_fwd_only", C.c_int64),
-                ("kernel_launches", C.c_int64), ("decoder_ms", C.c_float), ("total_ms", C.c_float)]
+                ("kernel_launches", C.c_int64), ("decoder_ms", C.c_float), ("total_ms", C.c_float),
+                ("solve_ms", C.c_float), ("pad_", C.c_float)]
 
 
 assert C.sizeof(ObjectOut) == 4 * RESULT_FLOATS

@@ -100,6 +100,8 @@ struct DspgnSolver {
   bool timing = false;
   std::vector<cudaEvent_t> ev;
   size_t ev_used = 0;
+  std::vector<cudaEvent_t> ev_solve;
+  size_t evs_used = 0;
   cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;
 };
 
@@ -234,7 +236,7 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
   CU(cudaFuncSetAttribute(k_decoder_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimtSmem)));
   if (int rc = tc_setup_kernels(g_err)) { delete s; return rc; }
   if (getenv("DSPGN_CLK")) {
-    const size_t nb = sizeof(long long) * kClkTiles * kTcMaxSteps * kClkSlots;
+    const size_t nb = sizeof(long long) * (kClkTiles * kTcMaxSteps * kClkSlots + 16);
     if (s->d_clk.reserve(nb)) { delete s; return fail(DSPGN_E_ALLOC, "cudaMalloc"); }
     CU(cudaMemset(s->d_clk.p, 0, nb));
     s->clk_on = true;
@@ -254,6 +256,7 @@ void dspgn_solver_destroy(DspgnSolver* s) {
   s->h_stage.release();
   s->h_results.release();
   for (auto e : s->ev) cudaEventDestroy(e);
+  for (auto e : s->ev_solve) cudaEventDestroy(e);
   if (s->ev_run0) cudaEventDestroy(s->ev_run0);
   if (s->ev_run1) cudaEventDestroy(s->ev_run1);
   delete s;
@@ -454,6 +457,7 @@ SolveArgs base_solve(DspgnSolver* s, int pose_only) {
   v.prm = SolverParams{c.k1, c.k2, c.k3, c.k4, c.b1, c.b2, c.lr, c.s_damp, c.code_len, c.num_depth_samples, c.cut_off, c.sdf_only};
   v.n_obj = s->n_obj; v.pose_only = pose_only; v.results = s->d_results.as<float>();
   v.dbg_obj = -1; v.dbg_H = nullptr; v.dbg_b = nullptr; v.dbg_dx = nullptr; v.dbg_loss = nullptr;
+  v.dbg_clk = s->clk_on ? s->d_clk.as<long long>() + kClkTiles * kTcMaxSteps * kClkSlots : nullptr;
   return v;
 }
 
@@ -468,13 +472,19 @@ int dspgn_run_batch(DspgnSolver* s, int mode) {
   const int iters = pose_only ? s->cfg.pose_only_iterations : s->cfg.num_iterations;
   s->ctr = DspgnCounters{};
   s->ev_used = 0;
+  s->evs_used = 0;
   CU(cudaEventRecord(s->ev_run0, s->stream));
   if (int rc = launch_init(s, pose_only)) return rc;
   for (int e = 0; e < iters; ++e) {
     if (int rc = launch_terms(s, pose_only, nullptr, nullptr, -1)) return rc;
     SolveArgs v = base_solve(s, pose_only);
     v.last_iter = (e == iters - 1); v.iter_index = e;
+    if (s->timing) {
+      if (s->evs_used + 2 > s->ev_solve.size()) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); s->ev_solve.push_back(e0); s->ev_solve.push_back(e1); }
+      cudaEventRecord(s->ev_solve[s->evs_used], s->stream);
+    }
     k_solve<<<s->n_obj, kSolveThreads, 0, s->stream>>>(v);
+    if (s->timing) { cudaEventRecord(s->ev_solve[s->evs_used + 1], s->stream); s->evs_used += 2; }
     s->ctr.kernel_launches++;
     CU(cudaGetLastError());
   }
@@ -496,6 +506,9 @@ int dspgn_results(DspgnSolver* s, DspgnObjectOut* out) {
     float dec = 0.f;
     for (size_t i = 0; i + 1 < s->ev_used; i += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]); dec += ms; }
     s->ctr.decoder_ms = dec;
+    float sv = 0.f;
+    for (size_t i = 0; i + 1 < s->evs_used; i += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, s->ev_solve[i], s->ev_solve[i + 1]); sv += ms; }
+    s->ctr.solve_ms = sv;
   }
   float tot = 0.f;
   if (cudaEventElapsedTime(&tot, s->ev_run0, s->ev_run1) == cudaSuccess) s->ctr.total_ms = tot; else cudaGetLastError();
@@ -583,7 +596,7 @@ int dspgn_debug_clocks(DspgnSolver* s, long long* out, int n) {
   // phase timeline of CTA 0's first tiles of the last SDF-term launch (enabled by env DSPGN_CLK=1 at solver creation)
   if (!s || !out) return fail(DSPGN_E_ARG, "null argument");
   if (!s->clk_on) return fail(DSPGN_E_ARG, "timeline not enabled (DSPGN_CLK)");
-  const int have = kClkTiles * kTcMaxSteps * kClkSlots;
+  const int have = kClkTiles * kTcMaxSteps * kClkSlots + 16;
   CU(cudaSetDevice(s->device));
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaMemcpy(out, s->d_clk.p, sizeof(long long) * (size_t)std::min(n, have), cudaMemcpyDeviceToHost));

@@ -58,11 +58,12 @@ struct SolveArgs {
   float* results;         // [n_obj][DSPGN_RESULT_FLOATS]
   // debug: dump the system of object dbg_obj and do not update any state
   int dbg_obj; float* dbg_H; float* dbg_b; float* dbg_dx; float* dbg_loss;
+  long long* dbg_clk;      // optional: 16 clock64 stamps of object 0's CTA
 };
 
 constexpr int kSolveThreads = 256;
 constexpr int kPMax = 7 + kMaxCode;   // 71
-constexpr int kHsStride = kPMax + 1;  // row stride of the factorisation workspace (doubles)
+constexpr int kAsStride = kPMax + 2;  // 73 floats: odd stride -> thread-per-row reads are bank-conflict free
 constexpr int kMaxEnt = (kPMax * (kPMax + 1) / 2 + kPMax + kSolveThreads - 1) / kSolveThreads;   // 11
 
 __device__ __forceinline__ int ext_to_int(int e, int npose, int L) {
@@ -90,13 +91,27 @@ __device__ void write_result(const SolveArgs& a, int o, const ObjState& st) {
   reinterpret_cast<int*>(r)[85] = 0;
 }
 
+constexpr int kElimThreads = 96;      // rows 0..70 live in the first three warps
+__device__ __forceinline__ void elim_bar() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+
+// 1/d for a positive finite double: fp32 reciprocal seed + two Newton steps (error ~ (2^-23)^4), ~5x cheaper
+// than the IEEE division on the critical path of every pivot
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x = (double)__frcp_rn((float)d);
+  x = x * (2.0 - d * x);
+  x = x * (2.0 - d * x);
+  return x;
+}
+
 // One CTA per object.  The normal system H dx = b (optimizer.py:161-186) is assembled in fp64 from the
 // fp64 accumulators and solved by an LDL^T factorisation in shared memory.  b rides along as row P of
 // the lower triangle, so after the factorisation that row holds the forward-substituted vector; each
 // thread owns a fixed set of <= 11 lower-triangle entries, one barrier per pivot.
 __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
-  __shared__ double Hs[(kPMax + 1) * kHsStride];
-  __shared__ double xs[kPMax];
+  __shared__ float As[kPMax * kAsStride];     // assembled augmented system [H | b], row i at i*kAsStride
+  __shared__ float4 bcast[2][(kPMax + 1) / 4 + 1];      // pivot row + rhs broadcast (double buffered)
+  __shared__ float ys[kPMax], rdiag[kPMax];
+  __shared__ float xs[kPMax];
   __shared__ float s_rot[4];       // J_rot.x, J_rot.z, res_rot, active
   __shared__ int s_flag;
   const int o = blockIdx.x, tid = threadIdx.x;
@@ -105,6 +120,8 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
   const int L = prm.code_len;
   const int npose = a.pose_only ? 6 : 7;
   const int P = a.pose_only ? 6 : (7 + L);
+#define SOLVE_CLK(k) do { if (a.dbg_clk != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.dbg_clk[k] = clock64(); } while (0)
+  SOLVE_CLK(0);
   const bool dbg = (a.dbg_H != nullptr);
   const bool use_render = !a.pose_only && !prm.sdf_only;
   // tile partials of this object, summed in tile order (deterministic), fp64
@@ -113,23 +130,35 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
   const int ntR = use_render ? (m + a.tile_rows - 1) / a.tile_rows : 0;
   const float* pS = a.part_s + (size_t)a.base_s[o] * kAccStride;
   const float* pR = use_render ? a.part_r + (size_t)a.base_r[o] * kAccStride : nullptr;
-  auto sumS = [&](int idx) { double v = 0.0; for (int t = 0; t < ntS; ++t) v += (double)pS[(size_t)t * kAccStride + idx]; return v; };
-  auto sumR = [&](int idx) { double v = 0.0; for (int t = 0; t < ntR; ++t) v += (double)pR[(size_t)t * kAccStride + idx]; return v; };
-
+  __shared__ double s_sum[4];      // sdf loss sum, sdf rows, render loss sum
   // ---- losses and the reference's soft-failure exits (optimizer.py:130-150) -----------------
   if (st.status != 0) {                          // frozen object: keep its record
     if (a.last_iter && tid == 0 && !dbg) write_result(a, o, st);
     return;
   }
-  const double nS = sumS(kAccLoss + 1);
-  const float sdf_loss = (float)(sumS(kAccLoss) / nS);
+  if (tid < 96) {
+    // three fixed-order reductions over the tiles (lane-strided partial sums + xor butterfly): warp 0: SDF
+    // loss, warp 1: SDF row count, warp 2: render loss
+    const int w = tid >> 5, ln = tid & 31;
+    const float* src = (w < 2) ? pS : pR;
+    const int nt = (w < 2) ? ntS : ntR, idx = (w == 1) ? kAccLoss + 1 : kAccLoss;
+    double v = 0.0;
+    for (int t = ln; t < nt; t += 32) v += (double)src[(size_t)t * kAccStride + idx];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (ln == 0) s_sum[w] = v;
+  }
+  __syncthreads();
+  SOLVE_CLK(1);
+  const double nS = s_sum[1];
+  const float sdf_loss = (float)(s_sum[0] / nS);
   float render_loss = 0.f;
   int status = 0;
   if (isnan(sdf_loss)) status = DSPGN_ST_SDF_NAN;
   else if (use_render) {
     if (V < 10) status = DSPGN_ST_RENDER_FEW;
     else {
-      render_loss = (m > 0) ? (float)(sumR(kAccLoss) / (double)m) : NAN;
+      render_loss = (m > 0) ? (float)(s_sum[2] / (double)m) : NAN;
       if (isnan(render_loss)) status = DSPGN_ST_RENDER_NAN;
     }
   }
@@ -168,31 +197,51 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
   }
   __syncthreads();
 
+  SOLVE_CLK(2);
   // ---- assemble the lower triangle of H and the b row (optimizer.py:161-184; pose-only: :68-71) ----
   const double wS = a.pose_only ? 1.0 / nS : (double)prm.k2 / nS;
   const double wR = use_render ? (double)prm.k1 / (double)m : 0.0;
   const int nTri = P * (P + 1) / 2, nEnt = nTri + P;
-  int ei[kMaxEnt], ej[kMaxEnt];
+  int ei[kMaxEnt], ej[kMaxEnt], eidx[kMaxEnt];
+  double accv[kMaxEnt], accr[kMaxEnt];
 #pragma unroll
   for (int q = 0; q < kMaxEnt; ++q) {
     const int e = tid + q * kSolveThreads;
-    int i = -1, j = 0;
+    int i = -1, j = 0, idx = 0;
     if (e < nTri) {
       i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
       while ((i + 1) * (i + 2) / 2 <= e) ++i;
       while (i * (i + 1) / 2 > e) --i;
       j = e - i * (i + 1) / 2;
+      int ri = ext_to_int(i, npose, L), ci = ext_to_int(j, npose, L);
+      if (ri > ci) { int t = ri; ri = ci; ci = t; }        // partials hold the upper triangle
+      idx = ri * kPInt + ci;
     } else if (e < nEnt) {
       i = P; j = e - nTri;
+      idx = kAccB + ext_to_int(j, npose, L);
     }
-    ei[q] = i; ej[q] = j;
+    ei[q] = i; ej[q] = j; eidx[q] = idx;
+    accv[q] = 0.0; accr[q] = 0.0;
+  }
+  // tile partials summed in tile order; the thread's (up to 11) entries give 11 independent loads per tile
+  for (int t = 0; t < ntS; ++t) {
+    const float* pt = pS + (size_t)t * kAccStride;
+#pragma unroll
+    for (int q = 0; q < kMaxEnt; ++q) if (ei[q] >= 0) accv[q] += (double)pt[eidx[q]];
+  }
+  for (int t = 0; t < ntR; ++t) {
+    const float* pt = pR + (size_t)t * kAccStride;
+#pragma unroll
+    for (int q = 0; q < kMaxEnt; ++q) if (ei[q] >= 0) accr[q] += (double)pt[eidx[q]];
+  }
+  SOLVE_CLK(3);
+#pragma unroll
+  for (int q = 0; q < kMaxEnt; ++q) {
+    const int i = ei[q], j = ej[q];
     if (i < 0) continue;
     double v;
     if (i < P) {
-      int ri = ext_to_int(i, npose, L), ci = ext_to_int(j, npose, L);
-      if (ri > ci) { int t = ri; ri = ci; ci = t; }        // accumulators hold the upper triangle
-      v = wS * sumS(ri * kPInt + ci);
-      if (use_render) v += wR * sumR(ri * kPInt + ci);
+      v = wS * accv[q] + wR * accr[q];
       if (a.pose_only) {
         if (i == j) v += 1e-2;                                           // optimizer.py:70
       } else {
@@ -207,9 +256,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
       }
       if (dbg && o == a.dbg_obj) { a.dbg_H[i * P + j] = (float)v; a.dbg_H[j * P + i] = (float)v; }
     } else {
-      const int ri = ext_to_int(j, npose, L);
-      v = -wS * sumS(kAccB + ri);
-      if (use_render) v -= wR * sumR(kAccB + ri);
+      v = -(wS * accv[q] + wR * accr[q]);
       if (!a.pose_only) {
         if (j >= 7) v -= (double)prm.k3 * (double)st.z[j - 7];           // optimizer.py:172
         if (s_rot[3] != 0.f && (j == 3 || j == 5))                       // optimizer.py:177-179 sign
@@ -217,43 +264,83 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
       }
       if (dbg && o == a.dbg_obj) a.dbg_b[j] = (float)v;
     }
-    Hs[i * kHsStride + j] = v;
+    if (i < P) { As[i * kAsStride + j] = (float)v; As[j * kAsStride + i] = (float)v; }
+    else As[j * kAsStride + kPMax] = (float)v;           // b_j -> augmented column
   }
   __syncthreads();
 
-  // ---- LDL^T: for pivot k, every entry (i,j) with j > k loses H[i][k] H[j][k] / d_k ------------------
-  for (int k = 0; k < P; ++k) {
-    const double d = Hs[k * kHsStride + k];
-    if (!(d > 0.0) || !isfinite(d)) { if (tid == 0) s_flag = 1; break; }    // uniform: all threads read the same d
-    const double inv = 1.0 / d;
-#pragma unroll
-    for (int q = 0; q < kMaxEnt; ++q) {
-      const int i = ei[q], j = ej[q];
-      if (i >= 0 && j > k) Hs[i * kHsStride + j] -= Hs[i * kHsStride + k] * Hs[j * kHsStride + k] * inv;
-    }
-    __syncthreads();
+  // padding rows/columns P..70 (pose-only: P = 6): identity, zero right-hand side
+  for (int idx = tid; idx < kPMax * (kPMax + 1); idx += kSolveThreads) {
+    const int i = idx / (kPMax + 1), j = idx - i * (kPMax + 1);
+    if (i >= P || (j >= P && j < kPMax)) As[i * kAsStride + j] = (i == j) ? 1.f : 0.f;
   }
   __syncthreads();
-  // ---- back substitution  L^T x = D^-1 w  (w = row P), column oriented -------------------------------
-  const bool bad = (s_flag != 0);
-  if (!bad) {
-    if (tid < P) xs[tid] = Hs[P * kHsStride + tid] / Hs[tid * kHsStride + tid];
-    __syncthreads();
-    for (int i = P - 1; i > 0; --i) {
-      const double xi = xs[i];
-      if (tid < i) xs[tid] -= (Hs[i * kHsStride + tid] / Hs[tid * kHsStride + tid]) * xi;
-      __syncthreads();
+  SOLVE_CLK(4);
+  // ---- Gaussian elimination of the SPD system, thread i = row i in registers; one barrier per pivot --------
+  if (tid < kElimThreads) {
+    // Thread i keeps row i of H in registers, rotated so that the current pivot column is always index 0:
+    // after pivot k, arow[j] holds H'[i][k+1+j].  The pivot loop stays rolled (small, cache-resident code)
+    // while every register index is a compile-time constant.  The broadcast pivot rows are the rows of U;
+    // they are parked in As (all rows were loaded into registers before the first barrier) for the
+    // back-substitution.
+    float arow[kPMax + 1];
+    const int row = (tid < kPMax) ? tid : kPMax - 1;        // lanes 71..95 mirror the last row (results unused)
+#pragma unroll
+    for (int j = 0; j < kPMax; ++j) arow[j] = As[row * kAsStride + j];
+    arow[kPMax] = 0.f;
+    float brow = As[row * kAsStride + kPMax];
+    int bad_pivot = 0;
+#pragma unroll 1
+    for (int k = 0; k < kPMax; ++k) {
+      float4* buf = bcast[k & 1];
+      if (tid == k) {
+#pragma unroll
+        for (int j = 0; j <= kPMax; j += 4) buf[j >> 2] = make_float4(arow[j], arow[j + 1], arow[j + 2], arow[j + 3]);
+        buf[(kPMax + 1) / 4] = make_float4(brow, 0.f, 0.f, 0.f);
+      }
+      elim_bar();
+      float pr[kPMax + 1];
+#pragma unroll
+      for (int j = 0; j <= kPMax; j += 4) {
+        const float4 v = buf[j >> 2];
+        pr[j] = v.x; pr[j + 1] = v.y; pr[j + 2] = v.z; pr[j + 3] = v.w;
+      }
+      const float pb = buf[(kPMax + 1) / 4].x;
+      const float piv = pr[0];
+      if (!(piv > 0.f) || !(piv < 3.0e38f)) bad_pivot = 1;        // every thread sees the same pivot
+      const float rpiv = __frcp_rn(piv);
+      // U[k][k + t] = pivot_row[t] (t < 71 - k), y_k = pb
+      if (tid < kPMax - k) As[k * kAsStride + k + tid] = reinterpret_cast<const float*>(buf)[tid];
+      if (tid == kElimThreads - 1) { ys[k] = pb; rdiag[k] = rpiv; }
+      if (tid > k) {
+        const float l = arow[0] * rpiv;
+#pragma unroll
+        for (int j = 1; j <= kPMax; ++j) arow[j - 1] = fmaf(-l, pr[j], arow[j]);
+        brow = fmaf(-l, pb, brow);
+      }
     }
-    if (tid < P && !isfinite(xs[tid])) s_flag = 1;
-    __syncthreads();
+    elim_bar();
+    // ---- back substitution  U x = y, column oriented, U and y in shared memory ----------------------------
+    float yreg = (tid < kPMax) ? ys[tid] : 0.f;
+#pragma unroll 1
+    for (int j = kPMax - 1; j >= 0; --j) {
+      if (tid == j) xs[j] = yreg * rdiag[j];
+      elim_bar();
+      if (tid < j) yreg = fmaf(-As[tid * kAsStride + j], xs[j], yreg);
+    }
+    if (bad_pivot && tid == 0) s_flag = 1;
   }
+  __syncthreads();
+  SOLVE_CLK(5);
+  if (tid < P && !isfinite(xs[tid])) s_flag = 1;
+  __syncthreads();
   if (dbg) {
-    if (o == a.dbg_obj && tid < P) a.dbg_dx[tid] = (float)xs[tid];
+    if (o == a.dbg_obj && tid < P) a.dbg_dx[tid] = xs[tid];
     return;
   }
   // ---- update (optimizer.py:186-192 / :72-74), clear accumulators, next depth range -----------
   const bool fail = (s_flag != 0);
-  if (!a.pose_only && tid < L && !fail) st.z[tid] += prm.lr * (float)xs[tid + 7];
+  if (!a.pose_only && tid < L && !fail) st.z[tid] += prm.lr * xs[tid + 7];
   if (tid == 0) {
     st.loss = loss; st.V = V; st.m = m;
     a.V_count[o] = 0;
@@ -261,7 +348,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
       st.status = DSPGN_ST_SOLVE;
     } else {
       float dp[7];
-      for (int i = 0; i < npose; ++i) dp[i] = (a.pose_only ? 1.0f : prm.lr) * (float)xs[i];
+      for (int i = 0; i < npose; ++i) dp[i] = (a.pose_only ? 1.0f : prm.lr) * xs[i];
       float dT[12], Tn[12];
       exp_sim3_dev(dp, !a.pose_only, dT);
       mul_affine(dT, st.T_oc, Tn);
@@ -271,6 +358,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
     }
     if (a.last_iter) write_result(a, o, st);
   }
+  SOLVE_CLK(6);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -144,7 +144,8 @@ class BatchSolver:
         c = _lib.Counters()
         _lib.check(_lib.load().dspgn_counters(self.handle, C.byref(c)))
         return dict(rows_fwd_bwd=c.rows_fwd_bwd, rows_fwd_only=c.rows_fwd_only,
-                    kernel_launches=c.kernel_launches, decoder_ms=c.decoder_ms, total_ms=c.total_ms)
+                    kernel_launches=c.kernel_launches, decoder_ms=c.decoder_ms, total_ms=c.total_ms,
+                    solve_ms=c.solve_ms)
 
     # whole calls ---------------------------------------------------------------------------------
     def reconstruct(self, objs):

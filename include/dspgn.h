@@ -152,6 +152,8 @@ typedef struct {
   int64_t kernel_launches;
   float decoder_ms;      /* device time of the decoder kernels of the last run (CUDA events), if timed */
   float total_ms;
+  float solve_ms;        /* device time of the per-object solve kernels of the last run, if timed */
+  float pad_;
 } DspgnCounters;
 int dspgn_counters(DspgnSolver* s, DspgnCounters* out);
 int dspgn_enable_timing(DspgnSolver* s, int on);

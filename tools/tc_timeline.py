@@ -21,3 +21,9 @@ for t in range(4):
     for s in range(17):
         r=a[t,s]-t0
         print(t, s, "|", r[4], r[5], "|", r[0], r[1], r[2], r[3], "| mma_issue", r[5]-r[4], "mma_run", r[0]-r[4], "epi", r[3]-r[0])
+n2=4*18*8+16
+buf2=(C.c_longlong*n2)()
+_lib.check(_lib.load().dspgn_debug_clocks(opt.solver.handle, buf2, n2))
+sv=np.array(buf2[4*18*8:])
+print("k_solve stamps (cycles from start): start, loss-reductions, rot-prior+sync, tile-partial loads, As fill, elimination+backsub, end")
+print((sv[:7]-sv[0]).tolist())
