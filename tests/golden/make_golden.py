@@ -253,5 +253,19 @@ def main():
     print("done")
 
 
+def voxel_golden():
+    """reconstruct/utils.py:97-117 voxel grid (with its true-division quirk) and decode_sdf on it."""
+    cars = load_ref_decoder("cars")
+    grid = ns.utils.create_voxel_grid(vol_dim=8)
+    z = torch.from_numpy(np.load(os.path.join(HERE, "stages.npz"))["sdf_z"])
+    sdf = ns.loss_utils.decode_sdf(cars, z, grid)
+    np.savez_compressed(os.path.join(HERE, "voxel.npz"), vox8=grid.numpy(), vox8_sdf=sdf.numpy(), z=z.numpy())
+    print("voxel.npz written")
+
+
 if __name__ == "__main__":
-    main()
+    if "--voxel-only" in sys.argv:
+        voxel_golden()
+    else:
+        main()
+        voxel_golden()

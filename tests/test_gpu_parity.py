@@ -161,6 +161,9 @@ def test_decode_sdf_and_mesh_grid(engine, stages, dec_path, oracle, oracle_decod
     grid = mx.sdf_grid(stages["sdf_z"])
     ref = oracle.decode_sdf(oracle_decoders["cars"], stages["sdf_z"], mx.voxel_points).reshape(8, 8, 8)
     np.testing.assert_allclose(grid, ref, rtol=0, atol=2e-6 if engine == "simt" else 2e-5)
+    # and against the reference's own grid decode (reconstruct/optimizer.py:214-217)
+    v = np.load(os.path.join(os.path.dirname(dec_path["cars"]), "voxel.npz"))
+    np.testing.assert_allclose(mx.sdf_grid(v["z"]).reshape(-1), v["vox8_sdf"], rtol=0, atol=2e-6 if engine == "simt" else 2e-5)
 
 
 @pytest.mark.parametrize("engine", ENGINES)

@@ -106,11 +106,11 @@ def test_config_keys_read_like_the_reference(cfg_kitti):
         Optimizer(object(), bad)
 
 
-def test_voxel_grid_quirk_matches_reference(stages):
+def test_voxel_grid_quirk_matches_reference(golden_dir):
+    """create_voxel_grid's integer-tensor true division (reconstruct/utils.py:107-108) reproduced."""
     from dsp_slam_b200.optimizer import create_voxel_grid
-    if "vox8" not in stages.files:
-        pytest.skip("golden without voxel grid")
-    np.testing.assert_allclose(create_voxel_grid(8), stages["vox8"], rtol=0, atol=1e-6)
+    v = np.load(os.path.join(golden_dir, "voxel.npz"))
+    np.testing.assert_allclose(create_voxel_grid(8), v["vox8"], rtol=0, atol=1e-6)
 
 
 def test_synth_is_deterministic_and_fortran_ordered():

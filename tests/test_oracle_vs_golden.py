@@ -143,3 +143,9 @@ def test_pose_only(oracle, oracle_decoders, cfg_kitti, golden_dir):
     cfg = oracle.GNConfig.from_json_dict(cfg_kitti)
     T = oracle.estimate_pose_cam_obj(oracle_decoders["cars"], cfg, d["in_t_co_se3"], float(d["in_scale"]), d["in_pts"], d["in_code"])
     np.testing.assert_allclose(T, d["t_cam_obj"], rtol=0, atol=2e-5)
+
+
+def test_decode_sdf_on_reference_voxel_grid(oracle, oracle_decoders, golden_dir):
+    v = np.load(os.path.join(golden_dir, "voxel.npz"))
+    s = oracle.decode_sdf(oracle_decoders["cars"], v["z"], v["vox8"])
+    np.testing.assert_allclose(s, v["vox8_sdf"], rtol=0, atol=2e-7)
