@@ -92,6 +92,10 @@ struct DspgnSolver {
   DevBuf d_state, d_part_s, d_part_r, d_tbase, d_V, d_m, d_results, d_active;
   DevBuf d_sdf, d_bx, d_bs, d_br;
   DevBuf d_dbg;
+  DevBuf d_q_items, d_q_flag, d_q_ctr, d_tiles_left, d_obj_iter;   // persistent-kernel work queue
+  int* d_tbase_static = nullptr;   // [n_obj] first 128-row tile of each object (inside the staging block)
+  int total_tiles128 = 0;
+  bool mega_enabled = true;
   DevBuf d_clk;
   bool clk_on = false;
   HostBuf h_results;
@@ -235,6 +239,7 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
   s->engine = eng;
   CU(cudaFuncSetAttribute(k_decoder_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimtSmem)));
   if (int rc = tc_setup_kernels(g_err)) { delete s; return rc; }
+  if (const char* m = getenv("DSPGN_MEGA")) s->mega_enabled = (m[0] != '0');
   if (getenv("DSPGN_CLK")) {
     const size_t nb = sizeof(long long) * (kClkTiles * kTcMaxSteps * kClkSlots + 16);
     if (s->d_clk.reserve(nb)) { delete s; return fail(DSPGN_E_ALLOC, "cudaMalloc"); }
@@ -252,7 +257,8 @@ void dspgn_solver_destroy(DspgnSolver* s) {
   cudaSetDevice(s->device);
   cudaDeviceSynchronize();
   for (DevBuf* b : {&s->d_decs, &s->d_stage, &s->d_state, &s->d_part_s, &s->d_part_r, &s->d_tbase, &s->d_V, &s->d_m, &s->d_results, &s->d_active,
-                    &s->d_sdf, &s->d_bx, &s->d_bs, &s->d_br, &s->d_dbg, &s->d_clk}) b->release();
+                    &s->d_sdf, &s->d_bx, &s->d_bs, &s->d_br, &s->d_dbg, &s->d_clk, &s->d_q_items, &s->d_q_flag, &s->d_q_ctr,
+                    &s->d_tiles_left, &s->d_obj_iter}) b->release();
   s->h_stage.release();
   s->h_results.release();
   for (auto e : s->ev) cudaEventDestroy(e);
@@ -306,7 +312,8 @@ int dspgn_upload_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in) {
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   const size_t o_meta = 0, o_T = al(o_meta + sizeof(ObjMeta) * n_obj), o_code = al(o_T + 64 * n_obj),
                o_pts = al(o_code + 4 * kMaxCode * (size_t)n_obj), o_rays = al(o_pts + 12 * (size_t)tp),
-               o_depth = al(o_rays + 12 * (size_t)tr), total = al(o_depth + 4 * (size_t)tf);
+               o_depth = al(o_rays + 12 * (size_t)tr), o_tb = al(o_depth + 4 * (size_t)tf),
+               total = al(o_tb + 4 * (size_t)n_obj);
   if (s->h_stage.reserve(total) || s->d_stage.reserve(total)) return fail(DSPGN_E_ALLOC, "staging allocation failed");
   unsigned char* hb = s->h_stage.as<unsigned char>();
   memcpy(hb + o_meta, s->h_meta.data(), sizeof(ObjMeta) * n_obj);
@@ -315,6 +322,12 @@ int dspgn_upload_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in) {
   float* hP = reinterpret_cast<float*>(hb + o_pts);
   float* hR = reinterpret_cast<float*>(hb + o_rays);
   float* hD = reinterpret_cast<float*>(hb + o_depth);
+  int* hTB = reinterpret_cast<int*>(hb + o_tb);
+  {
+    int acc = 0;
+    for (int o = 0; o < n_obj; ++o) { hTB[o] = acc; acc += (s->h_meta[o].n_pts + kTcRows - 1) / kTcRows; }
+    s->total_tiles128 = acc;
+  }
   for (int o = 0; o < n_obj; ++o) {
     const DspgnObjectIn& I = in[o];
     const ObjMeta& M = s->h_meta[o];
@@ -338,6 +351,7 @@ int dspgn_upload_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in) {
   s->d_pts = reinterpret_cast<float*>(db + o_pts);
   s->d_rays = reinterpret_cast<float*>(db + o_rays);
   s->d_depth = reinterpret_cast<float*>(db + o_depth);
+  s->d_tbase_static = reinterpret_cast<int*>(db + o_tb);
   s->n_obj = n_obj; s->tot_pts = (int)tp; s->tot_rays = (int)tr; s->tot_fg = (int)tf; s->tot_smp = ts; s->max_rays = max_rays;
   int bad = 0;
   bad |= s->d_state.reserve(sizeof(ObjState) * n_obj);
@@ -404,12 +418,19 @@ TermArgs base_term(DspgnSolver* s, int mode) {
   return a;
 }
 
-int launch_init(DspgnSolver* s, int pose_only) {
+int launch_init(DspgnSolver* s, int pose_only, bool mega = false) {
   InitArgs ia{};
   ia.meta = s->d_meta; ia.state = s->d_state.as<ObjState>(); ia.T_init = s->d_Tinit; ia.code_init = s->d_code;
   ia.V_count = s->d_V.as<int>(); ia.band_m = s->d_m.as<int>();
   ia.pt_active = nullptr; ia.n_obj = s->n_obj; ia.code_len = s->cfg.code_len; ia.D = s->cfg.num_depth_samples;
   ia.pose_only = pose_only;
+  ia.mega = mega ? 1 : 0;
+  if (mega) {
+    ia.tile_base = s->d_tbase_static; ia.tile_rows = kTcRows;
+    ia.q_items = s->d_q_items.as<int>(); ia.q_flag = s->d_q_flag.as<int>();
+    ia.q_head = s->d_q_ctr.as<int>(); ia.q_tail = s->d_q_ctr.as<int>() + 32; ia.done_objects = s->d_q_ctr.as<int>() + 64;
+    ia.tiles_left = s->d_tiles_left.as<int>(); ia.obj_iter = s->d_obj_iter.as<int>(); ia.total_tiles0 = s->total_tiles128;
+  }
   k_init<<<s->n_obj, 128, 0, s->stream>>>(ia);
   s->ctr.kernel_launches++;
   CU(cudaGetLastError());
@@ -474,6 +495,41 @@ int dspgn_run_batch(DspgnSolver* s, int mode) {
   s->ev_used = 0;
   s->evs_used = 0;
   CU(cudaEventRecord(s->ev_run0, s->stream));
+  const bool mega = s->mega_enabled && s->engine == DSPGN_ENGINE_TC && (pose_only || s->cfg.sdf_only) &&
+                    s->total_tiles128 > 0 && (long long)s->total_tiles128 * iters < (1LL << 28);
+  if (mega) {
+    // ---- persistent object-pipelined kernel: every GN iteration of every object in ONE launch --------------
+    const int cap = s->total_tiles128 * iters;
+    int bad = 0;
+    bad |= s->d_q_items.reserve(4 * (size_t)cap);
+    bad |= s->d_q_flag.reserve(4 * (size_t)cap);
+    bad |= s->d_q_ctr.reserve(4 * 96);
+    bad |= s->d_tiles_left.reserve(4 * (size_t)s->n_obj);
+    bad |= s->d_obj_iter.reserve(4 * (size_t)s->n_obj);
+    if (bad) return fail(DSPGN_E_ALLOC, "queue allocation failed");
+    CU(cudaMemsetAsync(s->d_q_flag.p, 0, 4 * (size_t)cap, s->stream));
+    if (int rc = launch_init(s, pose_only, true)) return rc;
+    TermArgs a = base_term(s, MODE_SDF);
+    a.huber_b = pose_only ? INFINITY : s->cfg.b2;
+    a.pose_only = pose_only;
+    a.tile_base = s->d_tbase_static;
+    a.dbg_clk = nullptr;
+    MegaArgs q{};
+    q.n_iters = iters; q.q_cap = cap;
+    q.q_items = s->d_q_items.as<int>(); q.q_flag = s->d_q_flag.as<int>();
+    q.q_head = s->d_q_ctr.as<int>(); q.q_tail = s->d_q_ctr.as<int>() + 32; q.done_objects = s->d_q_ctr.as<int>() + 64;
+    q.tiles_left = s->d_tiles_left.as<int>(); q.obj_iter = s->d_obj_iter.as<int>();
+    SolveArgs v = base_solve(s, pose_only);
+    v.base_s = s->d_tbase_static; v.tile_rows = kTcRows; v.last_iter = 0; v.iter_index = 0; v.dbg_clk = nullptr;
+    if (s->timing) cudaEventRecord(next_event(s), s->stream);
+    k_gn_persistent<<<s->num_sms, kTcThreads, kTcSmemBytes, s->stream>>>(a, q, v);
+    if (s->timing) cudaEventRecord(next_event(s), s->stream);
+    s->ctr.kernel_launches += 1;
+    s->ctr.rows_fwd_bwd += (long long)s->tot_pts * iters;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(s->ev_run1, s->stream));
+    return 0;
+  }
   if (int rc = launch_init(s, pose_only)) return rc;
   for (int e = 0; e < iters; ++e) {
     if (int rc = launch_terms(s, pose_only, nullptr, nullptr, -1)) return rc;

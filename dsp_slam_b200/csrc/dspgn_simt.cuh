@@ -56,6 +56,17 @@ struct TermArgs {
   long long* dbg_clk;         // optional phase timeline of CTA 0 (tensor-core engine)
 };
 
+// Device work queue of the persistent object-pipelined kernel (dspgn_tc.cuh): items = (object << 16 | tile).
+struct MegaArgs {
+  int n_iters;               // GN iterations per object
+  int q_cap;                 // total items that can ever be pushed (sum of tiles x iterations)
+  int* q_items; int* q_flag; // item payload / published flag per slot (no wrap-around)
+  int* q_head; int* q_tail;  // consumer ticket counter / producer reservation counter
+  int* tiles_left;           // [n_obj] tiles of the object's current iteration still running
+  int* obj_iter;             // [n_obj] current iteration of each object
+  int* done_objects;         // objects finished (last iteration or frozen)
+};
+
 // ---------------------------------------------------------------------------------------------
 // tile scheduling shared by all decoder kernels: rows per object -> tiles, scanned per CTA
 __device__ __forceinline__ int term_rows(const TermArgs& a, int o) {

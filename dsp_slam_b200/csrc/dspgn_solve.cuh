@@ -15,6 +15,9 @@ struct InitArgs {
   int* band_m;
   uint8_t* pt_active;      // [total_pts] reset to 1 (pose-only mode)
   int n_obj, code_len, D, pose_only;
+  // persistent-kernel mode: also seed the work queue with every object's iteration-0 tiles
+  int mega; const int* tile_base; int tile_rows; int* q_items; int* q_flag; int* q_head; int* q_tail;
+  int* tiles_left; int* obj_iter; int* done_objects; int total_tiles0;
 };
 
 __global__ void k_init(InitArgs a) {
@@ -36,6 +39,12 @@ __global__ void k_init(InitArgs a) {
     st.loss = 0.f; st.status = 0; st.iters = 0; st.V = 0; st.m = 0; st.n_active = M.n_pts;
     a.V_count[o] = 0;
     a.band_m[o] = 0;
+  }
+  if (a.mega) {
+    const int nt = (M.n_pts + a.tile_rows - 1) / a.tile_rows, base = a.tile_base[o];
+    for (int j = tid; j < nt; j += blockDim.x) { a.q_items[base + j] = (o << 16) | j; a.q_flag[base + j] = 1; }
+    if (tid == 0) { a.tiles_left[o] = nt; a.obj_iter[o] = 0; }
+    if (o == 0 && tid == 0) { *a.q_head = 0; *a.q_tail = a.total_tiles0; *a.done_objects = 0; }
   }
 }
 
@@ -61,6 +70,9 @@ struct SolveArgs {
   long long* dbg_clk;      // optional: 16 clock64 stamps of object 0's CTA
 };
 
+template <class T>
+__device__ __forceinline__ T ldv(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
+
 constexpr int kSolveThreads = 256;
 constexpr int kPMax = 7 + kMaxCode;   // 71
 constexpr int kAsStride = kPMax + 2;  // 73 floats: odd stride -> thread-per-row reads are bank-conflict free
@@ -73,8 +85,9 @@ __device__ __forceinline__ int ext_to_int(int e, int npose, int L) {
 
 __device__ void write_result(const SolveArgs& a, int o, const ObjState& st) {
   float* r = a.results + (size_t)o * DSPGN_RESULT_FLOATS;
-  float Tco[12];
-  inv_affine(st.T_oc, Tco, nullptr);                     // optimizer.py:200 / :83
+  float Toc[12], Tco[12];
+  for (int i = 0; i < 12; ++i) Toc[i] = ldv(&st.T_oc[i]);
+  inv_affine(Toc, Tco, nullptr);                         // optimizer.py:200 / :83
   if (a.pose_only) {                                     // optimizer.py:84: t_cam_obj[:3,:3] /= scale
     const float s = a.meta[o].scale;
     for (int i = 0; i < 3; ++i)
@@ -82,17 +95,35 @@ __device__ void write_result(const SolveArgs& a, int o, const ObjState& st) {
   }
   for (int i = 0; i < 12; ++i) r[i] = Tco[i];
   r[12] = 0.f; r[13] = 0.f; r[14] = 0.f; r[15] = 1.f;
-  for (int i = 0; i < kMaxCode; ++i) r[16 + i] = st.z[i];
-  r[80] = st.loss;
-  reinterpret_cast<int*>(r)[81] = st.status;
-  reinterpret_cast<int*>(r)[82] = st.V;
-  reinterpret_cast<int*>(r)[83] = st.m;
-  reinterpret_cast<int*>(r)[84] = st.iters;
+  for (int i = 0; i < kMaxCode; ++i) r[16 + i] = ldv(&st.z[i]);
+  r[80] = ldv(&st.loss);
+  reinterpret_cast<int*>(r)[81] = ldv(&st.status);
+  reinterpret_cast<int*>(r)[82] = ldv(&st.V);
+  reinterpret_cast<int*>(r)[83] = ldv(&st.m);
+  reinterpret_cast<int*>(r)[84] = ldv(&st.iters);
   reinterpret_cast<int*>(r)[85] = 0;
 }
 
 constexpr int kElimThreads = 96;      // rows 0..70 live in the first three warps
-__device__ __forceinline__ void elim_bar() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+__device__ __forceinline__ void elim_bar() { asm volatile("bar.sync 2, 96;" ::: "memory"); }
+
+// Shared-memory workspace of one solve (static in k_solve, carved from the J tile in the persistent kernel)
+struct SolveSmem {
+  float As[kPMax * kAsStride];                 // assembled augmented system [H | b]; later the rows of U
+  float4 bcast[2][(kPMax + 1) / 4 + 1];        // pivot row + rhs broadcast (double buffered)
+  float ys[kPMax], rdiag[kPMax], xs[kPMax];
+  float s_rot[4];                              // J_rot.x, J_rot.z, res_rot, active
+  double s_sum[4];                             // sdf loss sum, sdf rows, render loss sum
+  int s_flag;
+};
+
+// MEGA = called by the 256 epilogue threads of the persistent decoder kernel (named barrier, other CTAs wrote
+// the data: cache-bypassing loads); otherwise by the 256 threads of k_solve.
+template <bool MEGA>
+__device__ __forceinline__ void solve_sync() {
+  if (MEGA) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else __syncthreads();
+}
 
 // 1/d for a positive finite double: fp32 reciprocal seed + two Newton steps (error ~ (2^-23)^4), ~5x cheaper
 // than the IEEE division on the critical path of every pivot
@@ -103,24 +134,22 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return x;
 }
 
-// One CTA per object.  The normal system H dx = b (optimizer.py:161-186) is assembled in fp64 from the
-// fp64 accumulators and solved by an LDL^T factorisation in shared memory.  b rides along as row P of
-// the lower triangle, so after the factorisation that row holds the forward-substituted vector; each
-// thread owns a fixed set of <= 11 lower-triangle entries, one barrier per pivot.
-__global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
-  __shared__ float As[kPMax * kAsStride];     // assembled augmented system [H | b], row i at i*kAsStride
-  __shared__ float4 bcast[2][(kPMax + 1) / 4 + 1];      // pivot row + rhs broadcast (double buffered)
-  __shared__ float ys[kPMax], rdiag[kPMax];
-  __shared__ float xs[kPMax];
-  __shared__ float s_rot[4];       // J_rot.x, J_rot.z, res_rot, active
-  __shared__ int s_flag;
-  const int o = blockIdx.x, tid = threadIdx.x;
+// One CTA (or the epilogue half of one) per object: fixed-order reduction of the tile partials (fp64), priors
+// and damping (optimizer.py:161-184), Gaussian elimination of the SPD 71x71 system with thread = row in
+// registers, back-substitution, Sim(3)/SE(3) update, next depth range, soft failures (optimizer.py:130-150).
+// Returns 1 when the object is finished (last iteration, frozen or soft-failed), else 0.
+template <bool MEGA>
+__device__ int solve_object(const SolveArgs& a, const int o, const int tid, SolveSmem& SM, const bool last_iter) {
+  float (&As)[kPMax * kAsStride] = SM.As;
+  float4 (&bcast)[2][(kPMax + 1) / 4 + 1] = SM.bcast;
+  float (&ys)[kPMax] = SM.ys; float (&rdiag)[kPMax] = SM.rdiag; float (&xs)[kPMax] = SM.xs;
+  float (&s_rot)[4] = SM.s_rot; double (&s_sum)[4] = SM.s_sum; int& s_flag = SM.s_flag;
   ObjState& st = a.state[o];
   const SolverParams& prm = a.prm;
   const int L = prm.code_len;
   const int npose = a.pose_only ? 6 : 7;
   const int P = a.pose_only ? 6 : (7 + L);
-#define SOLVE_CLK(k) do { if (a.dbg_clk != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.dbg_clk[k] = clock64(); } while (0)
+#define SOLVE_CLK(k) do { if (!MEGA && a.dbg_clk != nullptr && o == 0 && tid == 0) a.dbg_clk[k] = clock64(); } while (0)
   SOLVE_CLK(0);
   const bool dbg = (a.dbg_H != nullptr);
   const bool use_render = !a.pose_only && !prm.sdf_only;
@@ -130,11 +159,10 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
   const int ntR = use_render ? (m + a.tile_rows - 1) / a.tile_rows : 0;
   const float* pS = a.part_s + (size_t)a.base_s[o] * kAccStride;
   const float* pR = use_render ? a.part_r + (size_t)a.base_r[o] * kAccStride : nullptr;
-  __shared__ double s_sum[4];      // sdf loss sum, sdf rows, render loss sum
   // ---- losses and the reference's soft-failure exits (optimizer.py:130-150) -----------------
-  if (st.status != 0) {                          // frozen object: keep its record
-    if (a.last_iter && tid == 0 && !dbg) write_result(a, o, st);
-    return;
+  if (ldv(&st.status) != 0) {                    // frozen object: keep its record
+    if (last_iter && tid == 0 && !dbg) write_result(a, o, st);
+    return 1;
   }
   if (tid < 96) {
     // three fixed-order reductions over the tiles (lane-strided partial sums + xor butterfly): warp 0: SDF
@@ -143,12 +171,12 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
     const float* src = (w < 2) ? pS : pR;
     const int nt = (w < 2) ? ntS : ntR, idx = (w == 1) ? kAccLoss + 1 : kAccLoss;
     double v = 0.0;
-    for (int t = ln; t < nt; t += 32) v += (double)src[(size_t)t * kAccStride + idx];
+    for (int t = ln; t < nt; t += 32) v += (double)__ldcg(src + (size_t)t * kAccStride + idx);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     if (ln == 0) s_sum[w] = v;
   }
-  __syncthreads();
+  solve_sync<MEGA>();
   SOLVE_CLK(1);
   const double nS = s_sum[1];
   const float sdf_loss = (float)(s_sum[0] / nS);
@@ -166,8 +194,8 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
     a.dbg_loss[0] = sdf_loss; a.dbg_loss[1] = render_loss; a.dbg_loss[2] = (float)V; a.dbg_loss[3] = (float)m;
   }
   if (status != 0) {
-    if (!dbg && tid == 0) { st.status = status; st.V = V; st.m = m; if (a.last_iter) write_result(a, o, st); }
-    return;
+    if (!dbg && tid == 0) { st.status = status; st.V = V; st.m = m; if (last_iter || MEGA) write_result(a, o, st); }
+    return 1;
   }
   const float loss = prm.k1 * render_loss + prm.k2 * sdf_loss;     // optimizer.py:155
 
@@ -176,9 +204,10 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
     s_rot[0] = s_rot[1] = s_rot[2] = s_rot[3] = 0.f;
     if (!a.pose_only) {
       // rotation prior (loss.py:155-178): r = 1 - (R_co e_y).n_g, n_g = (0,-1,0)
-      float Tco[12];
+      float Toc[12], Tco[12];
       double det_oc;
-      inv_affine(st.T_oc, Tco, &det_oc);
+      for (int i = 0; i < 12; ++i) Toc[i] = ldv(&st.T_oc[i]);
+      inv_affine(Toc, Tco, &det_oc);
       const float scale = powf((float)(1.0 / det_oc), 1.0f / 3.0f);
       float rco[12];
       for (int i = 0; i < 12; ++i) rco[i] = Tco[i] / scale;
@@ -195,7 +224,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
       }
     }
   }
-  __syncthreads();
+  solve_sync<MEGA>();
 
   SOLVE_CLK(2);
   // ---- assemble the lower triangle of H and the b row (optimizer.py:161-184; pose-only: :68-71) ----
@@ -227,12 +256,12 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
   for (int t = 0; t < ntS; ++t) {
     const float* pt = pS + (size_t)t * kAccStride;
 #pragma unroll
-    for (int q = 0; q < kMaxEnt; ++q) if (ei[q] >= 0) accv[q] += (double)pt[eidx[q]];
+    for (int q = 0; q < kMaxEnt; ++q) if (ei[q] >= 0) accv[q] += (double)__ldcg(pt + eidx[q]);
   }
   for (int t = 0; t < ntR; ++t) {
     const float* pt = pR + (size_t)t * kAccStride;
 #pragma unroll
-    for (int q = 0; q < kMaxEnt; ++q) if (ei[q] >= 0) accr[q] += (double)pt[eidx[q]];
+    for (int q = 0; q < kMaxEnt; ++q) if (ei[q] >= 0) accr[q] += (double)__ldcg(pt + eidx[q]);
   }
   SOLVE_CLK(3);
 #pragma unroll
@@ -258,7 +287,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
     } else {
       v = -(wS * accv[q] + wR * accr[q]);
       if (!a.pose_only) {
-        if (j >= 7) v -= (double)prm.k3 * (double)st.z[j - 7];           // optimizer.py:172
+        if (j >= 7) v -= (double)prm.k3 * (double)ldv(&st.z[j - 7]);     // optimizer.py:172
         if (s_rot[3] != 0.f && (j == 3 || j == 5))                       // optimizer.py:177-179 sign
           v += (double)prm.k4 * (double)(j == 3 ? s_rot[0] : s_rot[1]) * (double)s_rot[2];
       }
@@ -267,14 +296,14 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
     if (i < P) { As[i * kAsStride + j] = (float)v; As[j * kAsStride + i] = (float)v; }
     else As[j * kAsStride + kPMax] = (float)v;           // b_j -> augmented column
   }
-  __syncthreads();
+  solve_sync<MEGA>();
 
   // padding rows/columns P..70 (pose-only: P = 6): identity, zero right-hand side
   for (int idx = tid; idx < kPMax * (kPMax + 1); idx += kSolveThreads) {
     const int i = idx / (kPMax + 1), j = idx - i * (kPMax + 1);
     if (i >= P || (j >= P && j < kPMax)) As[i * kAsStride + j] = (i == j) ? 1.f : 0.f;
   }
-  __syncthreads();
+  solve_sync<MEGA>();
   SOLVE_CLK(4);
   // ---- Gaussian elimination of the SPD system, thread i = row i in registers; one barrier per pivot --------
   if (tid < kElimThreads) {
@@ -330,17 +359,18 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
     }
     if (bad_pivot && tid == 0) s_flag = 1;
   }
-  __syncthreads();
+  solve_sync<MEGA>();
   SOLVE_CLK(5);
   if (tid < P && !isfinite(xs[tid])) s_flag = 1;
-  __syncthreads();
+  solve_sync<MEGA>();
   if (dbg) {
     if (o == a.dbg_obj && tid < P) a.dbg_dx[tid] = xs[tid];
-    return;
+    return 1;
   }
   // ---- update (optimizer.py:186-192 / :72-74), clear accumulators, next depth range -----------
   const bool fail = (s_flag != 0);
-  if (!a.pose_only && tid < L && !fail) st.z[tid] += prm.lr * xs[tid + 7];
+  if (!a.pose_only && tid < L && !fail) st.z[tid] = ldv(&st.z[tid]) + prm.lr * xs[tid + 7];
+  solve_sync<MEGA>();                        // the result record below reads every z entry
   if (tid == 0) {
     st.loss = loss; st.V = V; st.m = m;
     a.V_count[o] = 0;
@@ -349,16 +379,23 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
     } else {
       float dp[7];
       for (int i = 0; i < npose; ++i) dp[i] = (a.pose_only ? 1.0f : prm.lr) * xs[i];
-      float dT[12], Tn[12];
+      float dT[12], Tn[12], Toc[12];
+      for (int i = 0; i < 12; ++i) Toc[i] = ldv(&st.T_oc[i]);
       exp_sim3_dev(dp, !a.pose_only, dT);
-      mul_affine(dT, st.T_oc, Tn);
+      mul_affine(dT, Toc, Tn);
       for (int i = 0; i < 12; ++i) st.T_oc[i] = Tn[i];
       derive_depth_range(st, prm.D);
-      st.iters += 1;
+      st.iters = ldv(&st.iters) + 1;
     }
-    if (a.last_iter) write_result(a, o, st);
+    if (last_iter || (MEGA && fail)) write_result(a, o, st);
   }
   SOLVE_CLK(6);
+  return (last_iter || fail) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
+  __shared__ SolveSmem SM;
+  solve_object<false>(a, blockIdx.x, threadIdx.x, SM, a.last_iter != 0);
 }
 
 // ---------------------------------------------------------------------------------------------

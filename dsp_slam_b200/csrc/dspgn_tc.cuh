@@ -24,6 +24,7 @@
 #include <string>
 #include <vector>
 #include "dspgn_simt.cuh"
+#include "dspgn_solve.cuh"
 
 namespace dspgn {
 
@@ -208,6 +209,7 @@ struct TcSmemTail {
   uint64_t a_ready[8];                    // 32-column unit u of the next A operand has been written
   uint32_t tmem_base;
   int cur_class;
+  int fifo[4]; int fifo_pub; int epi_seq; int last_flag;   // persistent mode: CTA-local tile FIFO (scheduler = producer warp)
   TcPlan plans[DSPGN_MAX_CLASSES];        // step plans of every decoder class (read by all warp roles)
 };
 constexpr size_t kTcSmemBytes = 1024 + (size_t)kTcStages * kTcStageBytes + sizeof(TcSmemTail);
@@ -240,13 +242,51 @@ __device__ __forceinline__ void unit_done(uint64_t* bar) {
   mbar_arrive(bar);
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
+struct TileRef { int o, row0, slot; };
+
+// pop one work item for this CTA (persistent mode); -1 = no more work anywhere
+__device__ inline int mega_pop(const MegaArgs& q, int n_obj) {
+  const int t = atomicAdd(q.q_head, 1);
+  if (t >= q.q_cap) return -1;
+  for (unsigned spins = 0;; ++spins) {
+    if (ldv(q.q_flag + t) != 0) { __threadfence(); return ldv(q.q_items + t); }
+    if (ldv(q.done_objects) >= n_obj) return -1;
+    __nanosleep(256);
+    if (spins > (1u << 24)) __trap();              // ~seconds: never hang the GPU on a logic error
+  }
+}
+
+// tile number `seq` of this CTA: static round-robin over the launch's tiles, or the CTA-local FIFO
+template <bool MEGA>
+__device__ __forceinline__ bool tile_at(const TermArgs& a, TcSmemTail& S, int seq, int total_tiles, TileRef& t) {
+  if (!MEGA) {
+    const int tile = blockIdx.x + seq * gridDim.x;
+    if (tile >= total_tiles) return false;
+    t.o = find_object(S.prefix, a.n_obj, tile);
+    t.row0 = (tile - S.prefix[t.o]) * kTcRows;
+    t.slot = tile;
+    return true;
+  } else {
+    volatile int* pub = &S.fifo_pub;
+    for (unsigned spins = 0; *pub <= seq; ++spins) { __nanosleep(64); if (spins > (1u << 26)) __trap(); }
+    const int item = reinterpret_cast<volatile int*>(S.fifo)[seq & 3];
+    if (item < 0) return false;
+    t.o = item >> 16;
+    const int j = item & 0xffff;
+    t.row0 = j * kTcRows;
+    t.slot = a.tile_base[t.o] + j;
+    return true;
+  }
+}
+
+template <bool MEGA>
+__device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, const SolveArgs& sv) {
   extern __shared__ unsigned char tc_smem_raw[];
   unsigned char* ring = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   TcSmemTail& S = *reinterpret_cast<TcSmemTail*>(ring + (size_t)kTcStages * kTcStageBytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  const int total_tiles = build_tile_prefix(a, kTcRows, S.prefix, S.warp_tmp);
+  const int total_tiles = MEGA ? 0 : build_tile_prefix(a, kTcRows, S.prefix, S.warp_tmp);
   {
     const int nwords = a.n_classes * (int)(sizeof(TcPlan) / 4);
     for (int i = tid; i < nwords; i += kTcThreads) {
@@ -259,6 +299,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
     mbar_init(&S.acc_full[0], 1);
     for (int i = 0; i < 8; ++i) mbar_init(&S.a_ready[i], 128);
     S.cur_class = -1;
+    S.fifo_pub = 0; S.epi_seq = 0; S.last_flag = 0;
     fence_barrier_init();
   }
   if (warp == 8) tc_alloc(&S.tmem_base, 512);
@@ -272,8 +313,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
     // ===================== weight producer ======================================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int o = find_object(S.prefix, a.n_obj, tile);
+      for (int seq = 0;; ++seq) {
+        if (MEGA) {
+          // scheduler: fetch this CTA's next tile into the local FIFO (at most 3 entries ahead of the epilogue)
+          volatile int* es = &S.epi_seq;
+          for (unsigned spins = 0; seq - *es >= 3; ++spins) { __nanosleep(64); if (spins > (1u << 26)) __trap(); }
+          const int item = mega_pop(q, a.n_obj);
+          reinterpret_cast<volatile int*>(S.fifo)[seq & 3] = item;
+          __threadfence_block();
+          *reinterpret_cast<volatile int*>(&S.fifo_pub) = seq + 1;
+        }
+        TileRef tr;
+        if (!tile_at<MEGA>(a, S, seq, total_tiles, tr)) break;
+        const int o = tr.o;
         const int cls = a.meta[o].class_id;
         const TcPlan& plan = S.plans[cls];
         const unsigned char* blob = a.decs[cls].tc_blob;
@@ -299,9 +351,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
     // per-unit a_ready barriers: K chunk c of a step only needs operand units 2c and 2c+1.
     uint32_t stage = 0, phase = 0, ar_phase = 0;
     int clk_tile = -1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int seq = 0;; ++seq) {
       ++clk_tile;
-      const int o = find_object(S.prefix, a.n_obj, tile);
+      TileRef tr;
+      if (!tile_at<MEGA>(a, S, seq, total_tiles, tr)) break;
+      const int o = tr.o;
       const TcPlan& plan = S.plans[a.meta[o].class_id];
       const int ns = fwd_only ? plan.n_fwd : plan.n_steps;
       for (int s = 0; s < ns; ++s) {
@@ -358,31 +412,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t acc_phase = 0;
     int clk_tile = -1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int seq = 0;; ++seq) {
       ++clk_tile;
-      const int o = find_object(S.prefix, a.n_obj, tile);
-      const int row0 = (tile - S.prefix[o]) * kTcRows;
+      TileRef tr;
+      if (!tile_at<MEGA>(a, S, seq, total_tiles, tr)) break;
+      if (MEGA && tid == 0) *reinterpret_cast<volatile int*>(&S.epi_seq) = seq + 1;
+      const int o = tr.o, row0 = tr.row0, tile = tr.slot;
       const ObjMeta M = a.meta[o];
       const ObjState& ost = a.state[o];
       const DecoderDev& dec = a.decs[M.class_id];
       const TcPlan& plan = S.plans[M.class_id];
       const int L = dec.L, in0 = dec.in0, n_lin = dec.n_lin;
       const bool has_skip = dec.latent_in >= 0;
-      const int nrows = min(kTcRows, term_rows(a, o) - row0);
+      const int nrows = min(kTcRows, (MEGA ? M.n_pts : term_rows(a, o)) - row0);
       const int ns = fwd_only ? plan.n_fwd : plan.n_steps;
+      // the pose / code of this object may have been rewritten by another CTA's solve: bypass L1
+      float Toc[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) Toc[i] = ldv(&ost.T_oc[i]);
 
       // ---- per-class constants in smem (bias, last row), the tile's latent code, this row's point ----
       if (S.cur_class != M.class_id) {
         for (int i = tid; i < n_lin * kHid; i += kTcEpiThreads) S.bias[i] = dec.bias[i / kHid][i % kHid];
         for (int i = tid; i < kHid; i += kTcEpiThreads) S.wlast[i] = dec.w_last[i];
       }
-      if (tid < kMaxCode + 16) S.zs[tid] = (tid < L) ? ost.z[tid] : 0.f;
+      if (tid < kMaxCode + 16) S.zs[tid] = (tid < L) ? ldv(&ost.z[tid]) : 0.f;
       float x0 = 0.f, x1 = 0.f, x2 = 0.f, sc = 0.f, res_in = 0.f;
       if (r < nrows) {
         const int rr_ = row0 + r;
         if (a.mode == MODE_SDF || a.mode == MODE_PTSFWD) {
           const float* q = a.pts + 3 * (size_t)(M.pts_off + rr_);
-          xform_point(ost.T_oc, q[0], q[1], q[2], x0, x1, x2);
+          xform_point(Toc, q[0], q[1], q[2], x0, x1, x2);
           sc = (a.pt_active == nullptr || a.pt_active[M.pts_off + rr_]) ? 1.f : 0.f;
         } else if (a.mode == MODE_BAND) {
           const size_t sidx = (size_t)M.smp_off + rr_;
@@ -392,7 +452,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
           const int ray = rr_ / a.D, j = rr_ - ray * a.D;
           const float* q = a.rays + 3 * (size_t)(M.ray_off + ray);
           const float d = lin_depth(ost.dmin, ost.dmax, ost.dstep, j, a.D);
-          xform_point(ost.T_oc, __fmul_rn(q[0], d), __fmul_rn(q[1], d), __fmul_rn(q[2], d), x0, x1, x2);
+          xform_point(Toc, __fmul_rn(q[0], d), __fmul_rn(q[1], d), __fmul_rn(q[2], d), x0, x1, x2);
           sc = (sqrtf(x0 * x0 + x1 * x1 + x2 * x2) < 1.0f) ? 1.f : 0.f;
         }
       }
@@ -630,12 +690,50 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
         }
         if (k == 0) { accp[kAccLoss] = sacc; accp[kAccLoss + 1] = n; }
       }
+      if (MEGA) {
+        // ---- object pipeline: the CTA that finishes an object's last tile solves its normal system, updates
+        // its pose/code and queues the tiles of its next iteration, while other objects keep the other SMs busy
+        __threadfence();                             // this tile's partial sums are visible device-wide
+        epi_bar_sync();
+        if (tid == 0) *reinterpret_cast<volatile int*>(&S.last_flag) = (atomicSub(q.tiles_left + o, 1) == 1) ? 1 : 0;
+        epi_bar_sync();
+        if (*reinterpret_cast<volatile int*>(&S.last_flag)) {
+          __threadfence();
+          SolveSmem& SM = *reinterpret_cast<SolveSmem*>(S.Jp);
+          const int it = ldv(q.obj_iter + o);
+          const int fin = solve_object<true>(sv, o, tid, SM, it + 1 >= q.n_iters);
+          epi_bar_sync();
+          if (tid == 0) {
+            __threadfence();                         // state / result record before anything is published
+            if (fin) {
+              atomicAdd(q.done_objects, 1);
+            } else {
+              const int nt = (M.n_pts + kTcRows - 1) / kTcRows;
+              *reinterpret_cast<volatile int*>(q.obj_iter + o) = it + 1;
+              *reinterpret_cast<volatile int*>(q.tiles_left + o) = nt;
+              __threadfence();
+              const int base = atomicAdd(q.q_tail, nt);
+              for (int j = 0; j < nt; ++j) *reinterpret_cast<volatile int*>(q.q_items + base + j) = (o << 16) | j;
+              __threadfence();
+              for (int j = 0; j < nt; ++j) *reinterpret_cast<volatile int*>(q.q_flag + base + j) = 1;
+            }
+          }
+        }
+      }
       // the next tile's prologue starts with epi_bar_sync(): Jp / rr are not rewritten before it
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tc_dealloc(tmem, 512);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
+  tc_body<false>(a, MegaArgs{}, SolveArgs{});
+}
+// persistent object-pipelined variant: all GN iterations of all objects in ONE launch (SDF term / pose-only)
+__global__ void __launch_bounds__(kTcThreads, 1) k_gn_persistent(TermArgs a, MegaArgs q, SolveArgs sv) {
+  tc_body<true>(a, q, sv);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -808,6 +906,10 @@ inline void tc_free_decoder(TcDecoderHost& h) {
 inline int tc_setup_kernels(std::string& err) {
   if (cudaFuncSetAttribute(k_decoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes) != cudaSuccess) {
     err = std::string("cudaFuncSetAttribute(k_decoder_tc): ") + cudaGetErrorString(cudaGetLastError());
+    return DSPGN_E_CUDA;
+  }
+  if (cudaFuncSetAttribute(k_gn_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes) != cudaSuccess) {
+    err = std::string("cudaFuncSetAttribute(k_gn_persistent): ") + cudaGetErrorString(cudaGetLastError());
     return DSPGN_E_CUDA;
   }
   if (cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTcStageBytes + 1024) != cudaSuccess) {
