@@ -221,6 +221,7 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   s->num_sms = prop.multiProcessorCount;
+  if (const char* g = getenv("DSPGN_GRID")) { int v = atoi(g); if (v >= 1 && v <= s->num_sms) s->num_sms = v; }   // experiments only
   for (int c = 0; c < n_classes; ++c) s->classes.push_back(classes[c]);
   std::vector<DecoderDev> decs;
   for (auto* d : s->classes) decs.push_back(d->dev);

@@ -61,6 +61,22 @@ def _strides(a):
     return [s // 4 for s in a.strides]
 
 
+def _as32(a):
+    return a if (type(a) is np.ndarray and a.dtype == np.float32) else np.asarray(a, dtype=np.float32)
+
+
+def _objectin_dtype():
+    names = [n for n, _ in _lib.ObjectIn._fields_]
+    fmt = {8: "<u8", 4: "<i4"}
+    return np.dtype({"names": names,
+                     "formats": ["<f4" if n == "scale" else fmt[getattr(_lib.ObjectIn, n).size] for n in names],
+                     "offsets": [getattr(_lib.ObjectIn, n).offset for n in names],
+                     "itemsize": C.sizeof(_lib.ObjectIn)})
+
+
+_OBJ_DT = _objectin_dtype()
+
+
 class BatchSolver:
     """Thin object wrapper over a DspgnSolver handle (one GPU)."""
 
@@ -87,40 +103,52 @@ class BatchSolver:
         _lib.check(_lib.load().dspgn_enable_timing(self.handle, int(on)))
 
     def _pack(self, objs):
+        """Marshal a list of object dicts into a DspgnObjectIn array (pointers + element strides; no data is
+        copied -- Fortran-ordered / strided float32 arrays are passed as they are).  Built as a numpy
+        structured array with the exact C layout (a per-field ctypes loop costs 2x more per call)."""
         n = len(objs)
-        arr = (_lib.ObjectIn * n)()
-        keep = []
-        for i, o in enumerate(objs):
-            T = _f32(o["t_cam_obj"])
-            P = _f32(o["pts"])
+        rec = np.zeros(n, dtype=_OBJ_DT)
+        Ts = [_as32(o["t_cam_obj"]) for o in objs]
+        Ps = [_as32(o["pts"]) for o in objs]
+        for T, P in zip(Ts, Ps):
             if T.shape != (4, 4) or P.ndim != 2 or P.shape[1] != 3:
                 raise ValueError("t_cam_obj must be (4,4) and pts (M,3)")
+        keep = [Ts, Ps]
+        rec["t_cam_obj"] = [a.ctypes.data for a in Ts]
+        st = np.array([a.strides for a in Ts], dtype=np.int64) >> 2
+        rec["t_rs"] = st[:, 0]; rec["t_cs"] = st[:, 1]
+        rec["pts"] = [a.ctypes.data for a in Ps]
+        sp = np.array([a.strides for a in Ps], dtype=np.int64) >> 2
+        rec["pts_rs"] = sp[:, 0]; rec["pts_cs"] = sp[:, 1]
+        rec["n_pts"] = [a.shape[0] for a in Ps]
+        rec["scale"] = 1.0
+        code_len = self.cfg.code_len
+        for i, o in enumerate(objs):                       # optional members
             R = o.get("rays")
-            D = o.get("depth")
-            Cd = o.get("code")
-            e = arr[i]
-            e.t_cam_obj = T.ctypes.data_as(_FP); e.t_rs, e.t_cs = _strides(T)
-            e.pts = P.ctypes.data_as(_FP); e.n_pts = P.shape[0]; e.pts_rs, e.pts_cs = _strides(P)
-            keep += [T, P]
             if R is not None and len(R):
-                R = _f32(R)
-                D = np.ascontiguousarray(_f32(D if D is not None else np.zeros(0))).reshape(-1)
-                e.rays = R.ctypes.data_as(_FP); e.n_rays = R.shape[0]; e.rays_rs, e.rays_cs = _strides(R)
-                e.depth = D.ctypes.data_as(_FP); e.n_depth = D.shape[0]
-                keep += [R, D]
-            else:
-                e.rays = None; e.n_rays = 0; e.depth = None; e.n_depth = 0
+                R = _as32(R)
+                D = o.get("depth")
+                D = np.ascontiguousarray(D if D is not None else np.zeros(0), dtype=np.float32).reshape(-1)
+                rs = R.strides
+                rec["rays"][i] = R.ctypes.data; rec["n_rays"][i] = R.shape[0]
+                rec["rays_rs"][i] = rs[0] >> 2; rec["rays_cs"][i] = rs[1] >> 2
+                rec["depth"][i] = D.ctypes.data; rec["n_depth"][i] = D.shape[0]
+                keep.append((R, D))
+            Cd = o.get("code")
             if Cd is not None:
-                Cd = np.ascontiguousarray(_f32(Cd)).reshape(-1)
-                if Cd.shape[0] < self.cfg.code_len:
+                Cd = np.ascontiguousarray(Cd, dtype=np.float32).reshape(-1)
+                if Cd.shape[0] < code_len:
                     raise ValueError("code shorter than code_len")
-                e.code = Cd.ctypes.data_as(_FP)
+                rec["code"][i] = Cd.ctypes.data
                 keep.append(Cd)
-            else:
-                e.code = None
-            e.scale = float(o.get("scale", 1.0))
-            e.class_id = int(o.get("class_id", 0))
-        return arr, keep
+            sc = o.get("scale")
+            if sc is not None:
+                rec["scale"][i] = float(sc)
+            cid = o.get("class_id")
+            if cid:
+                rec["class_id"][i] = int(cid)
+        keep.append(rec)
+        return rec.ctypes.data_as(C.POINTER(_lib.ObjectIn)), keep
 
     # three-phase API (resident batch) ----------------------------------------------------------
     def upload(self, objs):
@@ -197,14 +225,23 @@ class BatchSolver:
             pass
 
 
-def _unpack(rec, code_len, pose_only=False):
-    good = rec.status == _lib.ST_OK
-    if not good:
-        return ResultDict(t_cam_obj=None, code=None, is_good=False, loss=float(rec.loss), status=int(rec.status))
-    T = np.array(rec.t_cam_obj[:], dtype=np.float32).reshape(4, 4)
-    code = np.array(rec.code[:code_len], dtype=np.float32)
-    return ResultDict(t_cam_obj=T, code=code, is_good=True, loss=float(rec.loss), status=0,
-                      n_valid=int(rec.n_valid), n_band=int(rec.n_band))
+def _records(out, n):
+    """ctypes ObjectOut array -> (n, 88) float32 + int32 views (one copy)."""
+    rec = np.frombuffer(out, dtype=np.float32, count=n * _lib.RESULT_FLOATS).reshape(n, _lib.RESULT_FLOATS).copy()
+    return rec, rec.view(np.int32)
+
+
+def _unpack_all(out, n, code_len):
+    rec, ints = _records(out, n)
+    res = []
+    for i in range(n):
+        status = int(ints[i, 81])
+        if status != _lib.ST_OK:
+            res.append(ResultDict(t_cam_obj=None, code=None, is_good=False, loss=float(rec[i, 80]), status=status))
+        else:
+            res.append(ResultDict(t_cam_obj=rec[i, :16].reshape(4, 4), code=rec[i, 16:16 + code_len], is_good=True,
+                                  loss=float(rec[i, 80]), status=0, n_valid=int(ints[i, 82]), n_band=int(ints[i, 83])))
+    return res
 
 
 class Optimizer(object):
@@ -251,7 +288,7 @@ class Optimizer(object):
         is_good, loss)."""
         out = self.solver.reconstruct([dict(t_cam_obj=t_cam_obj, pts=pts, rays=rays, depth=depth,
                                             code=None if code is None else np.asarray(code)[:self.code_len])])
-        return _unpack(out[0], self.code_len)
+        return _unpack_all(out, 1, self.code_len)[0]
 
     def estimate_pose_cam_obj(self, t_co_se3, scale, pts, code):
         """optimizer.py:45-86.  Returns the optimised SE(3) object->camera transform, (4,4) f32."""
@@ -263,7 +300,7 @@ class Optimizer(object):
     def reconstruct_batch(self, objs):
         """objs: list of dicts(t_cam_obj, pts, rays, depth, [code], [class_id]) -> list of ResultDict."""
         out = self.solver.reconstruct(objs)
-        return [_unpack(out[i], self.code_len) for i in range(len(objs))]
+        return _unpack_all(out, len(objs), self.code_len)
 
     def estimate_pose_batch(self, objs):
         out = self.solver.estimate_pose(objs)
