@@ -206,7 +206,6 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
   if (!cfg || !classes || !out) return fail(DSPGN_E_ARG, "null argument");
   if (n_classes < 1 || n_classes > DSPGN_MAX_CLASSES) return fail(DSPGN_E_ARG, "n_classes must be in [1,4]");
   if (cfg->num_depth_samples < 2 || cfg->num_depth_samples > 64) return fail(DSPGN_E_ARG, "num_depth_samples must be in [2,64]");
-  if (cfg->pose_only_iterations > 5) return fail(DSPGN_E_ARG, "pose_only_iterations > 5 (inlier cut, optimizer.py:76-78) not supported");
   if (cfg->num_iterations < 1) return fail(DSPGN_E_ARG, "num_iterations must be >= 1");
   for (int c = 0; c < n_classes; ++c) {
     if (!classes[c] || classes[c]->device != device) return fail(DSPGN_E_ARG, "decoder/device mismatch");
@@ -408,7 +407,7 @@ TermArgs base_term(DspgnSolver* s, int mode) {
   TermArgs a{};
   a.meta = s->d_meta; a.state = s->d_state.as<ObjState>(); a.decs = s->d_decs.as<DecoderDev>();
   a.n_obj = s->n_obj; a.n_classes = (int)s->classes.size(); a.mode = mode;
-  a.pts = s->d_pts; a.pt_active = nullptr; a.rays = s->d_rays;
+  a.pts = s->d_pts; a.pt_active = nullptr; a.pt_active_out = nullptr; a.cut_iter = -1; a.rays = s->d_rays;
   a.band_x = s->d_bx.as<float>(); a.band_s = s->d_bs.as<float>(); a.band_r = s->d_br.as<float>();
   a.band_m = s->d_m.as<int>(); a.sdf_out = s->d_sdf.as<float>(); a.V_count = s->d_V.as<int>();
   a.part = (mode == MODE_BAND) ? s->d_part_r.as<float>() : (mode == MODE_SDF ? s->d_part_s.as<float>() : nullptr);
@@ -439,12 +438,16 @@ int launch_init(DspgnSolver* s, int pose_only, bool mega = false) {
 }
 
 // one GN iteration's residual-term kernels (everything before the solve)
-int launch_terms(DspgnSolver* s, int pose_only, float* dbg_J, float* dbg_res, int dbg_obj) {
+int launch_terms(DspgnSolver* s, int pose_only, float* dbg_J, float* dbg_res, int dbg_obj, int iter_index = 0) {
   const DspgnConfig& c = s->cfg;
   {
     TermArgs a = base_term(s, MODE_SDF);
     a.huber_b = pose_only ? INFINITY : c.b2;       // optimizer.py:71 uses raw residuals
     a.pose_only = pose_only;
+    if (pose_only) {                                   // optimizer.py:76-78: inlier cut taken after iteration index 4
+      if (iter_index == 4) a.pt_active_out = s->d_active.as<uint8_t>();
+      if (iter_index > 4) a.pt_active = s->d_active.as<uint8_t>();
+    }
     a.dbg_J = dbg_J; a.dbg_res = dbg_res; a.dbg_obj = dbg_obj; a.dbg_P = pose_only ? 6 : 7 + c.code_len;
     if (int rc = launch_term(s, a, s->tot_pts)) return rc;
     s->ctr.rows_fwd_bwd += s->tot_pts;
@@ -515,6 +518,7 @@ int dspgn_run_batch(DspgnSolver* s, int mode) {
     a.pose_only = pose_only;
     a.tile_base = s->d_tbase_static;
     a.dbg_clk = nullptr;
+    if (pose_only && iters > 5) { a.pt_active_out = s->d_active.as<uint8_t>(); a.cut_iter = 4; }
     MegaArgs q{};
     q.n_iters = iters; q.q_cap = cap;
     q.q_items = s->d_q_items.as<int>(); q.q_flag = s->d_q_flag.as<int>();
@@ -533,7 +537,7 @@ int dspgn_run_batch(DspgnSolver* s, int mode) {
   }
   if (int rc = launch_init(s, pose_only)) return rc;
   for (int e = 0; e < iters; ++e) {
-    if (int rc = launch_terms(s, pose_only, nullptr, nullptr, -1)) return rc;
+    if (int rc = launch_terms(s, pose_only, nullptr, nullptr, -1, e)) return rc;
     SolveArgs v = base_solve(s, pose_only);
     v.last_iter = (e == iters - 1); v.iter_index = e;
     if (s->timing) {

@@ -39,6 +39,8 @@ struct TermArgs {
   // sources
   const float* pts;          // MODE_SDF: camera-frame points (xyz interleaved)
   const uint8_t* pt_active;  // optional inlier mask (pose-only, optimizer.py:76-78), may be null
+  uint8_t* pt_active_out;    // when non-null: write |res| <= 0.05 per point (the cut taken after iteration index 4)
+  int cut_iter;              // persistent mode: object iteration at which the cut is recorded (4), -1 = never
   const float* rays;         // MODE_RAYFWD
   const float* band_x;       // MODE_BAND: object-frame points xyz interleaved, per-sample capacity
   const float* band_s;       // de_ds per band row
@@ -347,6 +349,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_decoder_simt(TermArgs a) {
       float res = (a.mode == MODE_SDF) ? S.yv[p] : S.rr[p];
       const float sc = S.rscale[p];
       if (sc == 0.f && (a.mode == MODE_SDF || p >= nrows)) res = 0.f;
+      if (a.pt_active_out != nullptr && a.mode == MODE_SDF && p < nrows)
+        a.pt_active_out[M.pts_off + row0 + p] = (sc != 0.f && fabsf(res) <= 0.05f) ? 1 : 0;   // optimizer.py:76-78
       S.yv[p] = res;                                        // raw residual (debug dump)
       S.rr[p] = huber_weight(fabsf(res), a.huber_b) * res;  // loss_utils.py:250-265
     }

@@ -374,7 +374,13 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
           mbar_wait(&S.a_ready[2 * c + 1], ar_phase);
           if (last)
             for (int u = 2 * c + 2; u < 8; ++u) mbar_wait(&S.a_ready[u], ar_phase);
-          if (c == 0 && lane == 0) DSPGN_CLK(4);
+          if (c == 0 && lane == 0) {
+            DSPGN_CLK(4);
+            if (a.dbg_clk != nullptr && blockIdx.x == 0 && clk_tile < kClkTiles) {
+              unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+              a.dbg_clk[((size_t)clk_tile * kTcMaxSteps + s) * kClkSlots + 6] = (long long)gt;
+            }
+          }
           // ---- W_hi image: A_hi*W_hi + A_lo*W_hi
           mbar_wait(&S.w_full[stage], phase);
           tc_fence_after();
@@ -437,13 +443,21 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         for (int i = tid; i < kHid; i += kTcEpiThreads) S.wlast[i] = dec.w_last[i];
       }
       if (tid < kMaxCode + 16) S.zs[tid] = (tid < L) ? ldv(&ost.z[tid]) : 0.f;
+      // pose-only inlier cut (optimizer.py:76-78): recorded while iteration `cut_iter` runs, applied afterwards
+      const uint8_t* mask_in = a.pt_active;
+      uint8_t* mask_out = a.pt_active_out;
+      if (MEGA && a.cut_iter >= 0) {
+        const int it_now = ldv(q.obj_iter + o);
+        mask_in = (it_now > a.cut_iter) ? a.pt_active_out : nullptr;
+        mask_out = (it_now == a.cut_iter) ? a.pt_active_out : nullptr;
+      }
       float x0 = 0.f, x1 = 0.f, x2 = 0.f, sc = 0.f, res_in = 0.f;
       if (r < nrows) {
         const int rr_ = row0 + r;
         if (a.mode == MODE_SDF || a.mode == MODE_PTSFWD) {
           const float* q = a.pts + 3 * (size_t)(M.pts_off + rr_);
           xform_point(Toc, q[0], q[1], q[2], x0, x1, x2);
-          sc = (a.pt_active == nullptr || a.pt_active[M.pts_off + rr_]) ? 1.f : 0.f;
+          sc = (mask_in == nullptr || ldv(mask_in + M.pts_off + rr_)) ? 1.f : 0.f;
         } else if (a.mode == MODE_BAND) {
           const size_t sidx = (size_t)M.smp_off + rr_;
           x0 = a.band_x[3 * sidx]; x1 = a.band_x[3 * sidx + 1]; x2 = a.band_x[3 * sidx + 2];
@@ -630,6 +644,8 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         jr[kMaxCode + 7] = 0.f;
         float res = (a.mode == MODE_SDF) ? yv : res_in;
         if (sc == 0.f && (a.mode == MODE_SDF || r >= nrows)) res = 0.f;
+        if (mask_out != nullptr && a.mode == MODE_SDF && r < nrows)
+          mask_out[M.pts_off + row0 + r] = (sc != 0.f && fabsf(res) <= 0.05f) ? 1 : 0;      // optimizer.py:76-78
         S.rr[r] = huber_weight(fabsf(res), a.huber_b) * res;
         S.rsc[r] = (a.mode == MODE_SDF) ? sc : (r < nrows ? 1.f : 0.f);
         if (a.dbg_J != nullptr && o == a.dbg_obj && a.mode == MODE_SDF && r < nrows) a.dbg_res[row0 + r] = res;

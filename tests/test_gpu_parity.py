@@ -249,3 +249,31 @@ def test_tc_operand_paths_selftest(n_mma, k_steps):
     ref = A.astype(np.float64) @ B.astype(np.float64).T
     err = np.abs(D - ref).max() / np.abs(ref).max()
     assert err < 5e-6, err
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_pose_only_inlier_cut_beyond_five_iterations(engine, dec_path, cfg_kitti, oracle, oracle_decoders):
+    """optimizer.py:76-78: after iteration index 4 points with |sdf| > 0.05 are dropped.  8 iterations,
+    10 % gross outliers, batch of 3 (persistent kernel for the tensor-core engine), vs the oracle."""
+    import copy
+    from dsp_slam_b200 import synth
+    cfg = copy.deepcopy(cfg_kitti)
+    cfg["optimizer"]["pose_only_optim"]["num_iterations"] = 8
+    opt = _engine_or_skip(engine, dec_path["cars"], cfg)
+    ocfg = oracle.GNConfig.from_json_dict(cfg)
+    ins, refs = [], []
+    for seed in (41, 42, 43):
+        o = synth.make_object(seed, 300)
+        pts = np.array(o["pts"])
+        rng = np.random.default_rng(seed)
+        bad = rng.choice(300, 30, replace=False)
+        pts[bad] += rng.normal(0, 0.6, size=(30, 3)).astype(np.float32)       # outliers
+        T = np.array(o["t_cam_obj_init"], dtype=np.float32)
+        s = float(np.cbrt(np.linalg.det(T[:3, :3].astype(np.float64))))
+        se3 = T.copy(); se3[:3, :3] /= s
+        code = (0.8 * o["code_gt"]).astype(np.float32)
+        ins.append(dict(t_cam_obj=se3, pts=np.asfortranarray(pts), code=code, scale=s))
+        refs.append(oracle.estimate_pose_cam_obj(oracle_decoders["cars"], ocfg, se3, s, pts, code))
+    outs = opt.estimate_pose_batch(ins)
+    for T, ref in zip(outs, refs):
+        np.testing.assert_allclose(T, ref, rtol=0, atol=2e-3)

@@ -27,3 +27,6 @@ _lib.check(_lib.load().dspgn_debug_clocks(opt.solver.handle, buf2, n2))
 sv=np.array(buf2[4*18*8:])
 print("k_solve stamps (cycles from start): start, loss-reductions, rot-prior+sync, tile-partial loads, As fill, elimination+backsub, end")
 print((sv[:7]-sv[0]).tolist())
+# effective SM clock during the kernel: clock64 vs %globaltimer (ns) between the first steps of tile 0 and tile 3
+dc = a[3,0,4]-a[0,0,4]; dg = a[3,0,6]-a[0,0,6]
+print("effective SM clock over tiles 0..3: %.3f GHz  (%d cycles in %d ns)" % (dc/max(dg,1), dc, dg))
