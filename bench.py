@@ -32,6 +32,8 @@ WORKLOADS = {
                  "BASELINE configs[1]: 32 objects x 2048 surface pts x 10 GN iters, surface-SDF loss"),
     "cfg2_full": (32, 2048, 2048, 200, "cars", "config_kitti.json", False,
                   "config 2 full: 32 objects x 2048 pts + 2248 rays x 50 depth samples x 10 GN iters"),
+    "slam1": (1, 250, 250, 200, "cars", "config_kitti.json", False,
+              "what LocalMapping sends per call (src/LocalMapping_util.cc:179-180): 1 object x 250 LiDAR pts + 450 rays x 50 samples x 10 iters"),
     "cfg3": (8, 256, 64, 18, "chairs", "config_redwood_01053.json", False,
              "BASELINE configs[2]: 8 chairs x 256 pts + 82 rays x 50 samples x 10 iters, initial code"),
 }

@@ -107,6 +107,8 @@ struct DspgnSolver {
   std::vector<cudaEvent_t> ev_solve;
   size_t evs_used = 0;
   cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;
+  cudaEvent_t ev_upload = nullptr;   // the pinned staging block may be rewritten only after its last H2D copy finished
+  bool upload_pending = false;
 };
 
 namespace {
@@ -246,6 +248,7 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
     CU(cudaMemset(s->d_clk.p, 0, nb));
     s->clk_on = true;
   }
+  CU(cudaEventCreateWithFlags(&s->ev_upload, cudaEventDisableTiming));
   CU(cudaEventCreate(&s->ev_run0));
   CU(cudaEventCreate(&s->ev_run1));
   *out = s;
@@ -263,6 +266,7 @@ void dspgn_solver_destroy(DspgnSolver* s) {
   s->h_results.release();
   for (auto e : s->ev) cudaEventDestroy(e);
   for (auto e : s->ev_solve) cudaEventDestroy(e);
+  if (s->ev_upload) cudaEventDestroy(s->ev_upload);
   if (s->ev_run0) cudaEventDestroy(s->ev_run0);
   if (s->ev_run1) cudaEventDestroy(s->ev_run1);
   delete s;
@@ -314,6 +318,8 @@ int dspgn_upload_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in) {
                o_pts = al(o_code + 4 * kMaxCode * (size_t)n_obj), o_rays = al(o_pts + 12 * (size_t)tp),
                o_depth = al(o_rays + 12 * (size_t)tr), o_tb = al(o_depth + 4 * (size_t)tf),
                total = al(o_tb + 4 * (size_t)n_obj);
+  if (s->upload_pending) { CU(cudaEventSynchronize(s->ev_upload)); s->upload_pending = false; }
+  if (s->d_stage.cap < total) CU(cudaStreamSynchronize(s->stream));      // kernels of an earlier batch may still read the old block
   if (s->h_stage.reserve(total) || s->d_stage.reserve(total)) return fail(DSPGN_E_ALLOC, "staging allocation failed");
   unsigned char* hb = s->h_stage.as<unsigned char>();
   memcpy(hb + o_meta, s->h_meta.data(), sizeof(ObjMeta) * n_obj);
@@ -344,6 +350,8 @@ int dspgn_upload_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in) {
     if (M.n_fg) memcpy(hD + M.fg_off, I.depth, 4 * (size_t)M.n_fg);
   }
   CU(cudaMemcpyAsync(s->d_stage.p, hb, total, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaEventRecord(s->ev_upload, s->stream));
+  s->upload_pending = true;
   unsigned char* db = s->d_stage.as<unsigned char>();
   s->d_meta = reinterpret_cast<ObjMeta*>(db + o_meta);
   s->d_Tinit = reinterpret_cast<float*>(db + o_T);

@@ -125,15 +125,6 @@ __device__ __forceinline__ void solve_sync() {
   else __syncthreads();
 }
 
-// 1/d for a positive finite double: fp32 reciprocal seed + two Newton steps (error ~ (2^-23)^4), ~5x cheaper
-// than the IEEE division on the critical path of every pivot
-__device__ __forceinline__ double fast_rcp(double d) {
-  double x = (double)__frcp_rn((float)d);
-  x = x * (2.0 - d * x);
-  x = x * (2.0 - d * x);
-  return x;
-}
-
 // One CTA (or the epilogue half of one) per object: fixed-order reduction of the tile partials (fp64), priors
 // and damping (optimizer.py:161-184), Gaussian elimination of the SPD 71x71 system with thread = row in
 // registers, back-substitution, Sim(3)/SE(3) update, next depth range, soft failures (optimizer.py:130-150).

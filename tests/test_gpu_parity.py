@@ -277,3 +277,18 @@ def test_pose_only_inlier_cut_beyond_five_iterations(engine, dec_path, cfg_kitti
     outs = opt.estimate_pose_batch(ins)
     for T, ref in zip(outs, refs):
         np.testing.assert_allclose(T, ref, rtol=0, atol=2e-3)
+
+
+def test_large_batch_256_objects_one_gpu(dec_path, cfg_kitti):
+    """BASELINE config 4's batch (256 x 2048 pts, SDF loss) on ONE GPU: all objects good, results equal to the
+    same objects solved in batches of 32 (the work queue / tile partial layout does not depend on batch size)."""
+    from dsp_slam_b200 import synth
+    objs = synth.make_batch(256, 2048)
+    ins = [dict(t_cam_obj=o["t_cam_obj_init"], pts=o["pts"]) for o in objs]
+    opt = _engine_or_skip("tc", dec_path["cars"], cfg_kitti, sdf_only=True)
+    big = opt.reconstruct_batch(ins)
+    assert all(r.is_good for r in big)
+    small = opt.reconstruct_batch(ins[64:96])
+    for a_, b_ in zip(big[64:96], small):
+        np.testing.assert_array_equal(a_.t_cam_obj, b_.t_cam_obj)
+        np.testing.assert_array_equal(a_.code, b_.code)
