@@ -107,6 +107,8 @@ struct DspgnSolver {
   std::vector<cudaEvent_t> ev_solve;
   size_t evs_used = 0;
   cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;
+  cudaStream_t stream2 = nullptr;    // fork: the ray-sample forward pass runs beside the SDF-row pass
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_upload = nullptr;   // the pinned staging block may be rewritten only after its last H2D copy finished
   bool upload_pending = false;
 };
@@ -249,6 +251,9 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
     s->clk_on = true;
   }
   CU(cudaEventCreateWithFlags(&s->ev_upload, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
   CU(cudaEventCreate(&s->ev_run0));
   CU(cudaEventCreate(&s->ev_run1));
   *out = s;
@@ -267,6 +272,9 @@ void dspgn_solver_destroy(DspgnSolver* s) {
   for (auto e : s->ev) cudaEventDestroy(e);
   for (auto e : s->ev_solve) cudaEventDestroy(e);
   if (s->ev_upload) cudaEventDestroy(s->ev_upload);
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->ev_join) cudaEventDestroy(s->ev_join);
+  if (s->stream2) cudaStreamDestroy(s->stream2);
   if (s->ev_run0) cudaEventDestroy(s->ev_run0);
   if (s->ev_run1) cudaEventDestroy(s->ev_run1);
   delete s;
@@ -394,18 +402,20 @@ cudaEvent_t next_event(DspgnSolver* s) {
   return s->ev[s->ev_used++];
 }
 
-int launch_term(DspgnSolver* s, TermArgs& a, long long rows_upper) {
-  if (s->timing) cudaEventRecord(next_event(s), s->stream);
+int launch_term(DspgnSolver* s, TermArgs& a, long long rows_upper, cudaStream_t stream = nullptr, bool use_given = false) {
+  cudaStream_t st = use_given ? stream : s->stream;
+  const bool timed = s->timing && !use_given;
+  if (timed) cudaEventRecord(next_event(s), st);
   const long long tile_rows = (s->engine == DSPGN_ENGINE_TC) ? kTcRows : kTP;
   long long tiles = (rows_upper + tile_rows - 1) / tile_rows + s->n_obj;
   if (s->engine == DSPGN_ENGINE_TC) {
-    if (int rc = tc_launch_term(a, s->num_sms, tiles, s->stream, g_err)) return rc;
+    if (int rc = tc_launch_term(a, s->num_sms, tiles, st, g_err)) return rc;
   } else {
     int grid = (int)std::min<long long>(tiles, s->num_sms);
     if (grid < 1) grid = 1;
-    k_decoder_simt<<<grid, kThreads, sizeof(SimtSmem), s->stream>>>(a);
+    k_decoder_simt<<<grid, kThreads, sizeof(SimtSmem), st>>>(a);
   }
-  if (s->timing) cudaEventRecord(next_event(s), s->stream);
+  if (timed) cudaEventRecord(next_event(s), st);
   s->ctr.kernel_launches++;
   CU(cudaGetLastError());
   return 0;
@@ -448,6 +458,23 @@ int launch_init(DspgnSolver* s, int pose_only, bool mega = false) {
 // one GN iteration's residual-term kernels (everything before the solve)
 int launch_terms(DspgnSolver* s, int pose_only, float* dbg_J, float* dbg_res, int dbg_obj, int iter_index = 0) {
   const DspgnConfig& c = s->cfg;
+  const bool render = !pose_only && !c.sdf_only;
+  // The SDF-row pass and the forward-only pass over the ray samples are independent: fork the latter onto a
+  // second stream (matters for small batches, where each pass is a single wave of tiles) unless per-launch
+  // timing is on.
+  const bool fork = render && !s->timing;
+  if (render) {
+    TermArgs f = base_term(s, MODE_RAYFWD);
+    if (fork) {
+      CU(cudaEventRecord(s->ev_fork, s->stream));
+      CU(cudaStreamWaitEvent(s->stream2, s->ev_fork, 0));
+      if (int rc = launch_term(s, f, s->tot_smp, s->stream2, true)) return rc;
+      CU(cudaEventRecord(s->ev_join, s->stream2));
+    } else {
+      if (int rc = launch_term(s, f, s->tot_smp)) return rc;
+    }
+    s->ctr.rows_fwd_only += s->tot_smp;
+  }
   {
     TermArgs a = base_term(s, MODE_SDF);
     a.huber_b = pose_only ? INFINITY : c.b2;       // optimizer.py:71 uses raw residuals
@@ -460,10 +487,8 @@ int launch_terms(DspgnSolver* s, int pose_only, float* dbg_J, float* dbg_res, in
     if (int rc = launch_term(s, a, s->tot_pts)) return rc;
     s->ctr.rows_fwd_bwd += s->tot_pts;
   }
-  if (!pose_only && !c.sdf_only) {
-    TermArgs f = base_term(s, MODE_RAYFWD);
-    if (int rc = launch_term(s, f, s->tot_smp)) return rc;
-    s->ctr.rows_fwd_only += s->tot_smp;
+  if (render) {
+    if (fork) CU(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
     ScanArgs sa{};
     sa.meta = s->d_meta; sa.state = s->d_state.as<ObjState>(); sa.rays = s->d_rays; sa.depth_fg = s->d_depth;
     sa.sdf = s->d_sdf.as<float>(); sa.band_x = s->d_bx.as<float>(); sa.band_s = s->d_bs.as<float>();
