@@ -292,3 +292,36 @@ def test_large_batch_256_objects_one_gpu(dec_path, cfg_kitti):
     for a_, b_ in zip(big[64:96], small):
         np.testing.assert_array_equal(a_.t_cam_obj, b_.t_cam_obj)
         np.testing.assert_array_equal(a_.code, b_.code)
+
+
+def test_mixed_classes_through_persistent_kernel(dec_path, cfg_kitti, oracle, oracle_decoders):
+    """BASELINE config 5 flavour: alternating cars / chairs (two resident weight sets), SDF loss, ragged sizes,
+    through the persistent object-pipelined kernel; every object vs the oracle with its own decoder."""
+    from dsp_slam_b200 import synth
+    clss = ["cars", "chairs"] * 6
+    sizes = [700, 129, 2048, 64, 1000, 333, 128, 2047, 5, 900, 1500, 256]
+    objs = [synth.make_object(60 + i, m, cls=c) for i, (m, c) in enumerate(zip(sizes, clss))]
+    opt = _engine_or_skip("tc", dec_path["cars"], cfg_kitti, sdf_only=True, extra_decoders=[dec_path["chairs"]])
+    rs = opt.reconstruct_batch([dict(t_cam_obj=o["t_cam_obj_init"], pts=o["pts"], class_id=(0 if c == "cars" else 1))
+                                for o, c in zip(objs, clss)])
+    ocfg = oracle.GNConfig.from_json_dict(cfg_kitti)
+    for o, r, c in zip(objs, rs, clss):
+        ref = oracle.reconstruct_object(oracle_decoders[c], ocfg, o["t_cam_obj_init"], o["pts"], None, None, sdf_only=True)
+        assert r.is_good and ref["is_good"]
+        # few points = weakly constrained problem = larger fp32 noise floor after 10 iterations (the fp32 SIMT
+        # engine shows the same 1e-2 on the 128/129-point objects, tools/diag_mixed.py)
+        m = o["pts"].shape[0]
+        assert np.abs(r.t_cam_obj - ref["t_cam_obj"]).max() < (3e-3 if m >= 500 else 2e-2)
+        assert np.abs(r.code - ref["code"]).max() < (1e-3 if m >= 500 else 4e-3)
+    # the persistent schedule and the per-iteration schedule are bit-identical
+    import os
+    os.environ["DSPGN_MEGA"] = "0"
+    try:
+        opt2 = _engine_or_skip("tc", dec_path["cars"], cfg_kitti, sdf_only=True, extra_decoders=[dec_path["chairs"]])
+        rs2 = opt2.reconstruct_batch([dict(t_cam_obj=o["t_cam_obj_init"], pts=o["pts"], class_id=(0 if c == "cars" else 1))
+                                      for o, c in zip(objs, clss)])
+    finally:
+        os.environ.pop("DSPGN_MEGA", None)
+    for a_, b_ in zip(rs, rs2):
+        np.testing.assert_array_equal(a_.t_cam_obj, b_.t_cam_obj)
+        np.testing.assert_array_equal(a_.code, b_.code)
