@@ -228,7 +228,7 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
   for (int c = 0; c < n_classes; ++c) s->classes.push_back(classes[c]);
   std::vector<DecoderDev> decs;
   for (auto* d : s->classes) decs.push_back(d->dev);
-  if (s->d_decs.reserve(decs.size() * sizeof(DecoderDev))) { delete s; return fail(DSPGN_E_ALLOC, "cudaMalloc"); }
+  if (s->d_decs.reserve(decs.size() * sizeof(DecoderDev))) { dspgn_solver_destroy(s); return fail(DSPGN_E_ALLOC, "cudaMalloc"); }
   CU(cudaMemcpy(s->d_decs.p, decs.data(), decs.size() * sizeof(DecoderDev), cudaMemcpyHostToDevice));
   bool tc_ok = true;
   for (auto* d : s->classes) tc_ok = tc_ok && d->tc.ok;
@@ -239,14 +239,14 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
     else if (e && !strcmp(e, "tc")) eng = DSPGN_ENGINE_TC;
     else eng = (tc_ok && tc_engine_default()) ? DSPGN_ENGINE_TC : DSPGN_ENGINE_SIMT;
   }
-  if (eng == DSPGN_ENGINE_TC && !tc_ok) { delete s; return fail(DSPGN_E_ARG, "tensor-core engine unavailable for this decoder shape"); }
+  if (eng == DSPGN_ENGINE_TC && !tc_ok) { dspgn_solver_destroy(s); return fail(DSPGN_E_ARG, "tensor-core engine unavailable for this decoder shape"); }
   s->engine = eng;
   CU(cudaFuncSetAttribute(k_decoder_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimtSmem)));
-  if (int rc = tc_setup_kernels(g_err)) { delete s; return rc; }
+  if (int rc = tc_setup_kernels(g_err)) { dspgn_solver_destroy(s); return rc; }
   if (const char* m = getenv("DSPGN_MEGA")) s->mega_enabled = (m[0] != '0');
   if (getenv("DSPGN_CLK")) {
     const size_t nb = sizeof(long long) * (kClkTiles * kTcMaxSteps * kClkSlots + 16);
-    if (s->d_clk.reserve(nb)) { delete s; return fail(DSPGN_E_ALLOC, "cudaMalloc"); }
+    if (s->d_clk.reserve(nb)) { dspgn_solver_destroy(s); return fail(DSPGN_E_ALLOC, "cudaMalloc"); }
     CU(cudaMemset(s->d_clk.p, 0, nb));
     s->clk_on = true;
   }
