@@ -325,3 +325,45 @@ def test_mixed_classes_through_persistent_kernel(dec_path, cfg_kitti, oracle, or
     for a_, b_ in zip(rs, rs2):
         np.testing.assert_array_equal(a_.t_cam_obj, b_.t_cam_obj)
         np.testing.assert_array_equal(a_.code, b_.code)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_code_len_32_decoder_single_step(engine, oracle, cfg_kitti):
+    """A 32-D latent decoder (the C++ side handles 32- or 64-D codes, src/LocalMapping_util.cc:415):
+    random weights, one GN step (SDF term) vs the oracle -- exercises the generic layer-shape handling
+    (in0 = 35, concat layer output 221, padded K/N) of both engines."""
+    import copy
+    from dsp_slam_b200 import synth
+    from dsp_slam_b200.decoder import DecoderWeights
+    from dsp_slam_b200.optimizer import Optimizer
+    from dsp_slam_b200._lib import DspgnError
+    rng = np.random.default_rng(5)
+    L, in0 = 32, 35
+    outs = [256, 256, 256, 256 - in0, 256, 256, 256, 256, 1]
+    ins_ = [in0, 256, 256, 256, 256, 256, 256, 256, 256]
+    W = [(rng.standard_normal((o, i)) * (1.2 / np.sqrt(i))).astype(np.float32) for o, i in zip(outs, ins_)]
+    b = [(rng.standard_normal(o) * 0.05).astype(np.float32) for o in outs]
+    W[-1] *= 0.2
+    cfg = copy.deepcopy(cfg_kitti)
+    cfg["optimizer"]["code_len"] = 32
+    dw = DecoderWeights(W, b, (4,), L)
+    try:
+        opt = Optimizer(dw, cfg, engine=engine, sdf_only=True)
+    except DspgnError as e:
+        if engine == "tc" and "unavailable" in str(e):
+            pytest.skip("tensor-core engine not available for this shape")
+        raise
+    o = synth.make_object(77, 500)
+    z0 = (0.1 * rng.standard_normal(32)).astype(np.float32)
+    opt.solver.upload([dict(t_cam_obj=o["t_cam_obj_init"], pts=o["pts"], code=z0)])
+    g = opt.solver.debug_system(0, 0, want_rows=True, n_pts=500)
+    odw = oracle.DecoderWeights(W, b, (4,), L)
+    ocfg = oracle.GNConfig.from_json_dict(cfg)
+    t_oc = oracle.inv4(o["t_cam_obj_init"])
+    J, res = oracle.sdf_term(odw, np.asarray(o["pts"]), t_oc, z0)
+    it = oracle.gn_iteration(odw, ocfg, t_oc, z0, np.asarray(o["pts"]), None, None, sdf_only=True)
+    tol = 1e-4 if engine == "simt" else 5e-4
+    assert g["J"].shape == (500, 39)
+    assert np.abs(g["res"] - res).max() < (1e-5 if engine == "simt" else 5e-5)
+    assert rel(g["J"], J) < (5e-5 if engine == "simt" else 5e-4)
+    assert rel(g["H"], it["H"]) < tol and rel(g["b"], it["b"]) < tol
