@@ -12,7 +12,7 @@ constexpr int kMaxCode = DSPGN_MAX_CODE;       // 64
 constexpr int kPInt = 72;                      // internal Jacobian row stride: [code 0..63 | pose 64..70 | pad]
 constexpr int kAccStride = kPInt * kPInt + kPInt + 8;  // floats per tile partial: H (upper) | b | {loss_sum, rows, ...}
 constexpr int kAccB = kPInt * kPInt;
-constexpr int kAccLoss = kAccB + kPInt;        // +0 loss sum, +1 row count (double)
+constexpr int kAccLoss = kAccB + kPInt;        // +0 loss sum, +1 row count
 constexpr int kTermSdf = 0, kTermRender = 1;
 
 // Static description of one object of the resident batch.
@@ -176,10 +176,6 @@ __device__ inline void mul_affine(const float* A, const float* B, float* out) {
       out[r * 4 + c] = acc;
     }
   }
-}
-
-__device__ __forceinline__ void atomic_add_f64(double* p, double v) {
-  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
 }  // namespace dspgn

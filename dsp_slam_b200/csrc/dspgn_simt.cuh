@@ -1,5 +1,5 @@
 // fp32 SIMT decoder engine: fused  transform -> DeepSDF forward -> backward-to-input -> Jacobian rows
-// -> J^T J / J^T r  for one 64-row tile per CTA iteration.  This engine is the on-device ground truth
+// -> per-tile partial sums of J^T J / J^T r  for one 64-row tile per CTA iteration.  This engine is the on-device ground truth
 // (plain FFMA, fp32 accumulation in k order) against which the tcgen05 engine is checked.
 //
 // Restates: loss.py:22-43 (SDF term), loss.py:143-150 (band rows of the render term),

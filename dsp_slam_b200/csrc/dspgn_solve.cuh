@@ -1,4 +1,5 @@
-// Per-object kernels: state initialisation, normal-equation assembly + solve + Sim(3)/SE(3) update,
+// Per-object code: state initialisation (+ work-queue seeding), normal-equation assembly from the tile partials,
+// register-resident elimination, Sim(3)/SE(3) update (kernel k_solve and device function solve_object),
 // and the per-ray occupancy scan / band compaction of the render term.
 // Restates optimizer.py:45-86, 97-203; loss.py:84-141, 155-178; loss_utils.py:188-233.
 #pragma once

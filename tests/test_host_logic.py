@@ -121,3 +121,57 @@ def test_synth_is_deterministic_and_fortran_ordered():
         np.testing.assert_array_equal(a[k], b[k])
         assert a[k].dtype == np.float32
     assert a["pts"].flags.f_contiguous and a["rays"].shape == (60, 3) and a["depth"].shape == (50,)
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_cuda():
+    """Argument validation of the C ABI returns DSPGN_E_ARG (-1) without needing a GPU."""
+    import ctypes as C
+    from dsp_slam_b200 import _lib
+    lib = _lib.load()
+    FP = C.POINTER(C.c_float)
+    h = C.c_void_p()
+    # null pointers
+    assert lib.dspgn_decoder_create(None, None, None, 0, C.byref(h)) == -1
+    assert b"null" in lib.dspgn_last_error()
+    # inconsistent decoder shapes
+    spec = _lib.DecoderSpec()
+    spec.latent_size = 64; spec.num_linear = 3; spec.latent_in_layer = -1
+    for k, (i, o) in enumerate([(67, 256), (200, 256), (256, 1)]):      # layer 1 in_dim != layer 0 out_dim
+        spec.in_dim[k], spec.out_dim[k] = i, o
+    W = [np.zeros((o, i), np.float32) for i, o in [(67, 256), (200, 256), (256, 1)]]
+    b = [np.zeros(o, np.float32) for o in (256, 256, 1)]
+    Wp = (FP * 3)(*[w.ctypes.data_as(FP) for w in W]); bp = (FP * 3)(*[x.ctypes.data_as(FP) for x in b])
+    assert lib.dspgn_decoder_create(C.byref(spec), Wp, bp, 0, C.byref(h)) == -1
+    assert b"in_dim" in lib.dspgn_last_error()
+    spec.in_dim[1] = 256
+    spec.out_dim[2] = 2                                                    # last layer must have one output
+    assert lib.dspgn_decoder_create(C.byref(spec), Wp, bp, 0, C.byref(h)) == -1
+    spec.out_dim[2] = 1
+    spec.latent_size = 65                                                  # > DSPGN_MAX_CODE
+    assert lib.dspgn_decoder_create(C.byref(spec), Wp, bp, 0, C.byref(h)) == -1
+    # solver / run entry points with null handles
+    assert lib.dspgn_run_batch(None, 0) == -1
+    assert lib.dspgn_upload_batch(None, 1, None) == -1
+    assert lib.dspgn_results(None, None) == -1
+    assert lib.dspgn_solver_engine(None) == -1
+    D = np.zeros((128, 16), np.float32)
+    assert lib.dspgn_tc_selftest(0, 17, 1, D.ctypes.data_as(FP), D.ctypes.data_as(FP), D.ctypes.data_as(FP)) == -1   # N % 16
+
+
+def test_optimizer_rejects_wrong_shapes(golden_dir, cfg_kitti):
+    """Misuse raises (ValueError) in the host layer; only per-object numerical failures are soft."""
+    from dsp_slam_b200.optimizer import BatchSolver
+    from dsp_slam_b200 import _lib
+    bs = BatchSolver.__new__(BatchSolver)
+    bs.cfg = _lib.Config(); bs.cfg.code_len = 64
+    with pytest.raises(ValueError):
+        bs._pack([dict(t_cam_obj=np.eye(3, dtype=np.float32), pts=np.zeros((5, 3), np.float32))])
+    with pytest.raises(ValueError):
+        bs._pack([dict(t_cam_obj=np.eye(4, dtype=np.float32), pts=np.zeros((5, 2), np.float32))])
+    with pytest.raises(ValueError):
+        bs._pack([dict(t_cam_obj=np.eye(4, dtype=np.float32), pts=np.zeros((5, 3), np.float32), code=np.zeros(10, np.float32))])
+    # float64 / list inputs are converted, Fortran order is passed through without a copy
+    P = np.asfortranarray(np.random.default_rng(0).standard_normal((7, 3)).astype(np.float32))
+    arr, keep = bs._pack([dict(t_cam_obj=np.eye(4).tolist(), pts=P)])
+    assert arr[0].n_pts == 7 and arr[0].pts_rs == 1 and arr[0].pts_cs == 7 and arr[0].t_rs == 4 and arr[0].t_cs == 1
+    assert arr[0].pts[arr[0].pts_cs * 2 + 3] == P[3, 2]
