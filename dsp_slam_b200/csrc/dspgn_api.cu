@@ -95,6 +95,7 @@ struct DspgnSolver {
   DevBuf d_q_items, d_q_flag, d_q_ctr, d_tiles_left, d_obj_iter;   // persistent-kernel work queue
   int* d_tbase_static = nullptr;   // [n_obj] first 128-row tile of each object (inside the staging block)
   int total_tiles128 = 0;
+  int max_tiles128 = 0;          // tiles of the largest object (work-queue items pack the tile index into 16 bits)
   bool mega_enabled = true;
   DevBuf d_clk;
   bool clk_on = false;
@@ -339,8 +340,12 @@ int dspgn_upload_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in) {
   int* hTB = reinterpret_cast<int*>(hb + o_tb);
   {
     int acc = 0;
-    for (int o = 0; o < n_obj; ++o) { hTB[o] = acc; acc += (s->h_meta[o].n_pts + kTcRows - 1) / kTcRows; }
-    s->total_tiles128 = acc;
+    int mx = 0;
+    for (int o = 0; o < n_obj; ++o) {
+      const int nt = (s->h_meta[o].n_pts + kTcRows - 1) / kTcRows;
+      hTB[o] = acc; acc += nt; if (nt > mx) mx = nt;
+    }
+    s->total_tiles128 = acc; s->max_tiles128 = mx;
   }
   for (int o = 0; o < n_obj; ++o) {
     const DspgnObjectIn& I = in[o];
@@ -533,7 +538,7 @@ int dspgn_run_batch(DspgnSolver* s, int mode) {
   s->evs_used = 0;
   CU(cudaEventRecord(s->ev_run0, s->stream));
   const bool mega = s->mega_enabled && s->engine == DSPGN_ENGINE_TC && (pose_only || s->cfg.sdf_only) &&
-                    s->total_tiles128 > 0 && (long long)s->total_tiles128 * iters < (1LL << 28);
+                    s->total_tiles128 > 0 && s->max_tiles128 <= 0xffff && (long long)s->total_tiles128 * iters < (1LL << 28);
   if (mega) {
     // ---- persistent object-pipelined kernel: every GN iteration of every object in ONE launch --------------
     const int cap = s->total_tiles128 * iters;
