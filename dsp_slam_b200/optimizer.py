@@ -349,14 +349,17 @@ class MeshExtractor(object):
         return s.reshape(self.voxels_dim, self.voxels_dim, self.voxels_dim)
 
     def extract_mesh_from_code(self, code):
+        """optimizer.py:214-223.  Marching cubes by scikit-image exactly like the reference when it is installed
+        (DSP-SLAM's own environment); otherwise the dependency-free marching-tetrahedra fallback of
+        dsp_slam_b200.mesh (same level set, different triangulation)."""
         sdf = self.sdf_grid(code)
+        voxel_size = 2.0 / (self.voxels_dim - 1)
         try:
             from skimage import measure
-        except ImportError as e:       # not installed in the build image; present in DSP-SLAM's env
-            raise ImportError("MeshExtractor needs scikit-image for marching cubes "
-                              "(reconstruct/utils.py:120-140); the SDF grid is available via sdf_grid()") from e
-        voxel_size = 2.0 / (self.voxels_dim - 1)
-        mc = getattr(measure, "marching_cubes_lewiner", None) or measure.marching_cubes
-        verts, faces, _, _ = mc(sdf, level=0.0, spacing=[voxel_size] * 3)
-        verts = verts + np.array([-1.0, -1.0, -1.0])
+            mc = getattr(measure, "marching_cubes_lewiner", None) or measure.marching_cubes
+            verts, faces, _, _ = mc(sdf, level=0.0, spacing=[voxel_size] * 3)
+        except ImportError:
+            from .mesh import marching_tetrahedra
+            verts, faces = marching_tetrahedra(sdf, level=0.0, spacing=[voxel_size] * 3)
+        verts = verts + np.array([-1.0, -1.0, -1.0])          # reconstruct/utils.py:131-137
         return ResultDict(vertices=verts.astype("float32"), faces=faces.astype("int32"))

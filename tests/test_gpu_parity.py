@@ -367,3 +367,23 @@ def test_code_len_32_decoder_single_step(engine, oracle, cfg_kitti):
     assert np.abs(g["res"] - res).max() < (1e-5 if engine == "simt" else 5e-5)
     assert rel(g["J"], J) < (5e-5 if engine == "simt" else 5e-4)
     assert rel(g["H"], it["H"]) < tol and rel(g["b"], it["b"]) < tol
+
+
+def test_extract_mesh_from_code_end_to_end(dec_path, stages, oracle, oracle_decoders):
+    """MeshExtractor.extract_mesh_from_code (reconstruct/optimizer.py:214-223): SDF grid on the GPU, iso-surface on
+    the host (scikit-image if installed, else the marching-tetrahedra fallback); compared with the same
+    extraction from the oracle's grid."""
+    from dsp_slam_b200.optimizer import MeshExtractor
+    from dsp_slam_b200.mesh import marching_tetrahedra
+    mx = MeshExtractor(dec_path["cars"], 64, 16)
+    m = mx.extract_mesh_from_code(stages["sdf_z"])
+    assert m.vertices.dtype == np.float32 and m.vertices.shape[1] == 3
+    assert m.faces.dtype == np.int32 and m.faces.shape[1] == 3 and m.faces.shape[0] > 100
+    assert m.faces.min() >= 0 and m.faces.max() < m.vertices.shape[0]
+    ref_grid = oracle.decode_sdf(oracle_decoders["cars"], stages["sdf_z"], mx.voxel_points).reshape(16, 16, 16)
+    try:
+        import skimage  # noqa: F401
+    except ImportError:
+        v, f = marching_tetrahedra(ref_grid, 0.0, [2.0 / 15] * 3)
+        assert abs(m.faces.shape[0] - f.shape[0]) <= 0.02 * f.shape[0] + 4
+        assert abs(m.vertices.mean(axis=0) - (v.mean(axis=0) - 1.0)).max() < 2e-3
