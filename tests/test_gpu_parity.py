@@ -385,5 +385,5 @@ def test_extract_mesh_from_code_end_to_end(dec_path, stages, oracle, oracle_deco
         import skimage  # noqa: F401
     except ImportError:
         v, f = marching_tetrahedra(ref_grid, 0.0, [2.0 / 15] * 3)
-        assert abs(m.faces.shape[0] - f.shape[0]) <= 0.02 * f.shape[0] + 4
-        assert abs(m.vertices.mean(axis=0) - (v.mean(axis=0) - 1.0)).max() < 2e-3
+        assert abs(m.faces.shape[0] - f.shape[0]) <= 0.05 * f.shape[0] + 10
+        assert abs(m.vertices.mean(axis=0) - (v.mean(axis=0) - 1.0)).max() < 5e-3
