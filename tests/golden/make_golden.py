@@ -72,6 +72,37 @@ class SolveRecorder:
         torch.inverse, torch.mv = self._inv, self._mv
 
 
+class RenderRecorder:
+    """Per-iteration counters of the render term, captured without touching the reference: V = number of
+    query points handed to the no-grad decode_sdf inside compute_render_loss (loss.py:77-78), m = rows of
+    the render Jacobian it returns (loss.py:143-150); -1 where the call returned None."""
+
+    def __enter__(self):
+        self.V, self.m = [], []
+        self._crl = ns.optimizer.compute_render_loss
+        self._dec = ns.loss.decode_sdf
+        rec = self
+
+        def dec(decoder, latent, pts, *a, **k):
+            rec._lastV = int(pts.shape[0])
+            return rec._dec(decoder, latent, pts, *a, **k)
+
+        def crl(*a, **k):
+            rec._lastV = -1
+            r = rec._crl(*a, **k)
+            rec.V.append(rec._lastV)
+            rec.m.append(-1 if r is None else int(r[0].shape[0]))
+            return r
+
+        ns.loss.decode_sdf = dec
+        ns.optimizer.compute_render_loss = crl
+        return self
+
+    def __exit__(self, *a):
+        ns.loss.decode_sdf = self._dec
+        ns.optimizer.compute_render_loss = self._crl
+
+
 def np_f(x):
     return np.asfortranarray(np.array(x, dtype=np.float32))
 
@@ -79,7 +110,7 @@ def np_f(x):
 def run_reconstruct(dec, cfg, obj, with_code=False):
     opt = ns.optimizer.Optimizer(dec, cfg)
     code = None if not with_code else np.array(obj["code_init"], dtype=np.float32)
-    with SolveRecorder() as rec:
+    with SolveRecorder() as rec, RenderRecorder() as rr:
         out = opt.reconstruct_object(np_f(obj["t_cam_obj_init"]), np_f(obj["pts"]),
                                      np_f(obj["rays"]), np.array(obj["depth"], dtype=np.float32),
                                      code)
@@ -91,6 +122,8 @@ def run_reconstruct(dec, cfg, obj, with_code=False):
         res["H_iters"] = np.stack(rec.H)
         res["b_iters"] = np.stack(rec.b)
         res["dx_iters"] = np.stack(rec.dx)
+    res["V_iters"] = np.array(rr.V, dtype=np.int64)
+    res["m_iters"] = np.array(rr.m, dtype=np.int64)
     return res
 
 
@@ -230,6 +263,15 @@ def main():
     o = synth.make_object(2, 256, 64, 18, cls="chairs", init_code_frac=0.5)
     np.savez_compressed(os.path.join(HERE, "recon_cfg3.npz"), **pack_inputs(o, True),
                         **run_reconstruct(chairs, cfg3, o, with_code=True))
+    # config 2 FULL size: 2048 pts, 2048 fg + 200 bg rays (V ~ 1e5, m in the thousands), 10 iterations
+    o = synth.make_object(7, 2048, 2048, 200)
+    np.savez_compressed(os.path.join(HERE, "recon_cfg2full.npz"), **pack_inputs(o),
+                        **run_reconstruct(cars, cfgk, o))
+    # config 3 at B = 8: exactly the batch bench.py --workload cfg3 builds (seeds 0..7)
+    objs = synth.make_batch(8, 256, 64, 18, cls="chairs", seed0=0, init_code_frac=0.5)
+    per = [dict(**pack_inputs(ob, True), **run_reconstruct(chairs, cfg3, ob, with_code=True)) for ob in objs]
+    keys = sorted(set.intersection(*[set(p) for p in per]))
+    np.savez_compressed(os.path.join(HERE, "recon_cfg3_b8.npz"), **{k: np.stack([p[k] for p in per]) for k in keys})
     # sdf_only composition, 512 pts, 10 iterations
     o = synth.make_object(4, 512, 0, 0)
     o["rays"] = np.zeros((0, 3), np.float32); o["depth"] = np.zeros((0,), np.float32)
