@@ -11,7 +11,9 @@ MAX_LINEAR = 12
 RESULT_FLOATS = 88
 
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
-ST_OK, ST_SDF_NAN, ST_RENDER_FEW, ST_RENDER_NAN, ST_SOLVE = 0, 1, 2, 3, 4
+ST_OK, ST_SDF_NAN, ST_RENDER_FEW, ST_RENDER_NAN, ST_SOLVE, ST_BAD_INPUT = 0, 1, 2, 3, 4, 5
+E_ARG, E_CUDA, E_NOGPU, E_ALLOC, E_PEER = -1, -2, -3, -4, -5
+IPC_HANDLE_BYTES = 64
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdspgn.so")
@@ -54,6 +56,10 @@ class Counters(C.Structure):
                 ("solve_ms", C.c_float), ("pad_", C.c_float)]
 
 
+class IpcHandle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * IPC_HANDLE_BYTES)]
+
+
 assert C.sizeof(ObjectOut) == 4 * RESULT_FLOATS
 
 # every symbol include/dspgn.h declares: (name, restype, argtypes)
@@ -67,6 +73,7 @@ SYMBOLS = [
     ("dspgn_solver_destroy", None, [_VP]),
     ("dspgn_solver_set_stream", C.c_int, [_VP, _VP]),
     ("dspgn_solver_engine", C.c_int, [_VP]),
+    ("dspgn_solver_sync", C.c_int, [_VP]),
     ("dspgn_reconstruct_batch", C.c_int, [_VP, C.c_int, C.POINTER(ObjectIn), C.POINTER(ObjectOut)]),
     ("dspgn_estimate_pose_batch", C.c_int, [_VP, C.c_int, C.POINTER(ObjectIn), C.POINTER(ObjectOut)]),
     ("dspgn_upload_batch", C.c_int, [_VP, C.c_int, C.POINTER(ObjectIn)]),
@@ -76,7 +83,17 @@ SYMBOLS = [
     ("dspgn_decode_sdf", C.c_int, [_VP, C.c_int, _FP, _FP, C.c_int, C.c_int, C.c_int, _FP]),
     ("dspgn_counters", C.c_int, [_VP, C.POINTER(Counters)]),
     ("dspgn_enable_timing", C.c_int, [_VP, C.c_int]),
+    ("dspgn_gather_create", C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(IpcHandle)]),
+    ("dspgn_gather_open", C.c_int, [_VP, C.POINTER(IpcHandle), C.c_int, C.c_int, C.c_int]),
+    ("dspgn_gather_bind", C.c_int, [_VP, C.POINTER(C.c_int32), C.c_int]),
+    ("dspgn_run_batch_gather", C.c_int, [_VP, C.c_int, C.c_int]),
+    ("dspgn_gather_results", C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(ObjectOut)]),
+    ("dspgn_gather_device", _VP, [_VP, C.c_int]),
+    ("dspgn_gather_wait_ns", C.c_longlong, [_VP]),
+    ("dspgn_gather_close", None, [_VP]),
+    ("dspgn_debug_exp", C.c_int, [C.c_int, C.c_int, _FP, C.c_int, _FP]),
     ("dspgn_debug_system", C.c_int, [_VP, C.c_int, C.c_int, _FP, _FP, _FP, _FP, _FP, _FP]),
+    ("dspgn_debug_system_iter", C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _FP, _FP, _FP, _FP, _FP, _FP]),
     ("dspgn_debug_clocks", C.c_int, [_VP, C.POINTER(C.c_longlong), C.c_int]),
     ("dspgn_tc_selftest", C.c_int, [C.c_int, C.c_int, C.c_int, _FP, _FP, _FP]),
 ]
@@ -109,4 +126,6 @@ def load():
 def check(rc):
     if rc != 0:
         msg = load().dspgn_last_error()
-        raise DspgnError(f"libdspgn error {rc}: {msg.decode() if msg else ''}")
+        err = DspgnError(f"libdspgn error {rc}: {msg.decode() if msg else ''}")
+        err.code = rc
+        raise err

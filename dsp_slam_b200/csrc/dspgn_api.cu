@@ -112,6 +112,18 @@ struct DspgnSolver {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_upload = nullptr;   // the pinned staging block may be rewritten only after its last H2D copy finished
   bool upload_pending = false;
+  int n_bad = 0;                     // resident objects rejected at upload (status BAD_INPUT, never evaluated)
+  // multi-GPU result exchange (rank 0 owns the buffer, the others map it through CUDA IPC)
+  struct Gather {
+    bool active = false, owner = false;
+    unsigned char* base = nullptr;   // [2][n_slots][88] floats | flags[world] | ack
+    int n_slots = 0, world = 0, rank = 0;
+    size_t off_flags = 0, off_ack = 0;
+    DevBuf d_slot_of, d_local;       // d_local: int err | long long wait_ns
+    HostBuf h_out;
+    int bound_n = -1;
+  } gather;
+  GatherDev gdev{};                  // exchange arguments of the run being enqueued (slots == nullptr: off)
 };
 
 namespace {
@@ -215,11 +227,23 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
   for (int c = 0; c < n_classes; ++c) {
     if (!classes[c] || classes[c]->device != device) return fail(DSPGN_E_ARG, "decoder/device mismatch");
     if (cfg->code_len < 1 || cfg->code_len > classes[c]->spec.latent_size) return fail(DSPGN_E_ARG, "code_len exceeds decoder latent_size");
-    if (cfg->code_len != classes[c]->spec.latent_size) return fail(DSPGN_E_ARG, "code_len must equal the decoder latent_size");
+    // code_len < latent_size: the trailing latent entries stay zero and are not optimised (optimizer.py:97-100
+    // slices code[:code_len]; the reference itself needs code_len == latent size for its decoder input)
   }
   CU(cudaSetDevice(device));
   DspgnSolver* s = new (std::nothrow) DspgnSolver();
   if (!s) return fail(DSPGN_E_ALLOC, "oom");
+  // every failure below releases the half-built solver (events, streams, device buffers)
+#undef CU
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      const int rc_ = fail(DSPGN_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+      dspgn_solver_destroy(s);                                                            \
+      return rc_;                                                                         \
+    }                                                                                     \
+  } while (0)
   s->device = device;
   s->cfg = *cfg;
   cudaDeviceProp prop;
@@ -257,6 +281,13 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
   CU(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
   CU(cudaEventCreate(&s->ev_run0));
   CU(cudaEventCreate(&s->ev_run1));
+#undef CU
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(DSPGN_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+  } while (0)
   *out = s;
   return 0;
 }
@@ -265,6 +296,7 @@ void dspgn_solver_destroy(DspgnSolver* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   cudaDeviceSynchronize();
+  dspgn_gather_close(s);
   for (DevBuf* b : {&s->d_decs, &s->d_stage, &s->d_state, &s->d_part_s, &s->d_part_r, &s->d_tbase, &s->d_V, &s->d_m, &s->d_results, &s->d_active,
                     &s->d_sdf, &s->d_bx, &s->d_bs, &s->d_br, &s->d_dbg, &s->d_clk, &s->d_q_items, &s->d_q_flag, &s->d_q_ctr,
                     &s->d_tiles_left, &s->d_obj_iter}) b->release();
@@ -289,37 +321,57 @@ int dspgn_solver_set_stream(DspgnSolver* s, void* cuda_stream) {
 
 int dspgn_solver_engine(const DspgnSolver* s) { return s ? s->engine : DSPGN_E_ARG; }
 
+int dspgn_solver_sync(DspgnSolver* s) {
+  if (!s) return fail(DSPGN_E_ARG, "null solver");
+  CU(cudaSetDevice(s->device));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
 int dspgn_enable_timing(DspgnSolver* s, int on) { if (!s) return fail(DSPGN_E_ARG, "null solver"); s->timing = on != 0; return 0; }
 
 int dspgn_counters(DspgnSolver* s, DspgnCounters* out) {
   if (!s || !out) return fail(DSPGN_E_ARG, "null argument");
+  // device time of the last run's kernels, if they have finished (events on the solver's stream)
+  float tot = 0.f;
+  if (s->ev_run0 && s->ev_run1 && cudaEventElapsedTime(&tot, s->ev_run0, s->ev_run1) == cudaSuccess) s->ctr.total_ms = tot;
+  else cudaGetLastError();
   *out = s->ctr;
   return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-int dspgn_upload_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in) {
+namespace {
+
+// decode_only: forward-only use (dspgn_decode_sdf) -- no J^T J partials, no band buffers
+int upload_batch_impl(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, bool decode_only) {
   if (!s || !in) return fail(DSPGN_E_ARG, "null argument");
-  if (n_obj < 1 || n_obj > kMaxObjScan) return fail(DSPGN_E_ARG, "n_obj must be in [1,1024]");
+  if (n_obj < 1 || n_obj > kMaxObjScan) return fail(DSPGN_E_ARG, "n_obj must be in [1,1024] per resident batch");
   CU(cudaSetDevice(s->device));
   const int D = s->cfg.num_depth_samples;
   s->h_meta.assign(n_obj, ObjMeta{});
   long long tp = 0, tr = 0, tf = 0, ts = 0;
-  int max_rays = 0;
+  int max_rays = 0, n_bad = 0;
   for (int o = 0; o < n_obj; ++o) {
     const DspgnObjectIn& I = in[o];
-    if (!I.t_cam_obj || I.n_pts < 1 || !I.pts) return fail(DSPGN_E_ARG, "object needs a pose and at least one surface point");
-    if (I.n_rays < 0 || I.n_depth < 0 || I.n_depth > I.n_rays) return fail(DSPGN_E_ARG, "n_depth must be <= n_rays");
-    if (I.n_rays > kScanMaxRays) return fail(DSPGN_E_ARG, "n_rays must be <= 8192");
+    // misuse of the API fails the call; an unusable DETECTION only fails that object (status BAD_INPUT ->
+    // is_good=False), like the reference's soft exits (optimizer.py:130-150): one bad object must neither abort
+    // its batch neighbours nor raise inside the embedded interpreter
+    if (!I.t_cam_obj) return fail(DSPGN_E_ARG, "object without a pose");
     if (I.class_id < 0 || I.class_id >= (int)s->classes.size()) return fail(DSPGN_E_ARG, "bad class_id");
+    const bool bad = I.n_pts < 1 || !I.pts || I.n_rays < 0 || I.n_depth < 0 || I.n_depth > I.n_rays ||
+                     I.n_rays > kScanMaxRays || (I.n_rays > 0 && I.n_depth > 0 && !I.depth);
     ObjMeta& M = s->h_meta[o];
-    M.pts_off = (int)tp; M.n_pts = I.n_pts;
-    M.ray_off = (int)tr; M.n_rays = I.rays ? I.n_rays : 0; M.n_fg = I.rays ? I.n_depth : 0;
+    M.bad = bad ? 1 : 0;
+    M.pts_off = (int)tp; M.n_pts = bad ? 0 : I.n_pts;
+    M.ray_off = (int)tr; M.n_rays = (!bad && I.rays) ? I.n_rays : 0; M.n_fg = (!bad && I.rays) ? I.n_depth : 0;
     M.fg_off = (int)tf; M.smp_off = (int)ts;
     M.class_id = I.class_id; M.scale = I.scale; M.has_code = I.code != nullptr;
     tp += M.n_pts; tr += M.n_rays; tf += M.n_fg; ts += (long long)M.n_rays * D;
     if (M.n_rays > max_rays) max_rays = M.n_rays;
+    n_bad += M.bad;
   }
+  s->n_bad = n_bad;
   if (tp > (1 << 28) || ts > (1LL << 30)) return fail(DSPGN_E_ARG, "batch too large");
   // one staging block: meta | T_init | code | pts | rays | depth
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
@@ -354,7 +406,7 @@ int dspgn_upload_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in) {
       for (int c = 0; c < 4; ++c) hT[o * 16 + r * 4 + c] = I.t_cam_obj[(size_t)r * I.t_rs + (size_t)c * I.t_cs];
     for (int i = 0; i < kMaxCode; ++i) hC[o * kMaxCode + i] = (I.code && i < s->cfg.code_len) ? I.code[i] : 0.f;
     float* p = hP + 3 * (size_t)M.pts_off;
-    if (I.pts_cs == 1 && I.pts_rs == 3) memcpy(p, I.pts, 12 * (size_t)M.n_pts);
+    if (M.n_pts > 0 && I.pts_cs == 1 && I.pts_rs == 3) memcpy(p, I.pts, 12 * (size_t)M.n_pts);
     else for (int r = 0; r < M.n_pts; ++r)
       for (int c = 0; c < 3; ++c) p[3 * (size_t)r + c] = I.pts[(size_t)r * I.pts_rs + (size_t)c * I.pts_cs];
     float* q = hR + 3 * (size_t)M.ray_off;
@@ -374,22 +426,25 @@ int dspgn_upload_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in) {
   s->d_depth = reinterpret_cast<float*>(db + o_depth);
   s->d_tbase_static = reinterpret_cast<int*>(db + o_tb);
   s->n_obj = n_obj; s->tot_pts = (int)tp; s->tot_rays = (int)tr; s->tot_fg = (int)tf; s->tot_smp = ts; s->max_rays = max_rays;
+  s->gather.bound_n = -1;
   int bad = 0;
   bad |= s->d_state.reserve(sizeof(ObjState) * n_obj);
-  {
-    // per-tile partial sums: one slot per possible tile of each term (rows/tile of the smaller-tile engine)
-    const size_t tiles_s = (size_t)tp / kTP + n_obj + 1, tiles_r = (size_t)ts / kTP + n_obj + 1;
+  const bool render = !decode_only && !s->cfg.sdf_only;
+  if (!decode_only) {
+    // per-tile partial sums: one slot per possible tile of each term at the engine's tile height
+    const size_t rows_per_tile = (s->engine == DSPGN_ENGINE_TC) ? kTcRows : kTP;
+    const size_t tiles_s = (size_t)tp / rows_per_tile + n_obj + 1, tiles_r = (size_t)ts / rows_per_tile + n_obj + 1;
     bad |= s->d_part_s.reserve(4 * (size_t)kAccStride * tiles_s);
-    if (!s->cfg.sdf_only) bad |= s->d_part_r.reserve(4 * (size_t)kAccStride * tiles_r);
-    bad |= s->d_tbase.reserve(4 * 2 * (size_t)n_obj);
+    if (render) bad |= s->d_part_r.reserve(4 * (size_t)kAccStride * tiles_r);
+    bad |= s->d_active.reserve((size_t)tp + 1);
   }
+  bad |= s->d_tbase.reserve(4 * 2 * (size_t)n_obj);
   bad |= s->d_V.reserve(4 * (size_t)n_obj);
   bad |= s->d_m.reserve(4 * (size_t)n_obj);
   bad |= s->d_results.reserve(4 * DSPGN_RESULT_FLOATS * (size_t)n_obj);
   bad |= s->h_results.reserve(4 * DSPGN_RESULT_FLOATS * (size_t)n_obj);
-  bad |= s->d_active.reserve((size_t)tp);
   const size_t smp = (size_t)(ts > 0 ? ts : 1);
-  if (!s->cfg.sdf_only) {
+  if (render) {
     bad |= s->d_sdf.reserve(4 * smp);
     bad |= s->d_bx.reserve(12 * smp);
     bad |= s->d_bs.reserve(4 * smp);
@@ -398,6 +453,12 @@ int dspgn_upload_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in) {
   bad |= s->d_dbg.reserve(4 * ((size_t)kPMax * kPMax + 2 * kPMax + 8));
   if (bad) return fail(DSPGN_E_ALLOC, "workspace allocation failed");
   return 0;
+}
+
+}  // namespace
+
+int dspgn_upload_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in) {
+  return upload_batch_impl(s, n_obj, in, false);
 }
 
 namespace {
@@ -447,6 +508,7 @@ int launch_init(DspgnSolver* s, int pose_only, bool mega = false) {
   ia.V_count = s->d_V.as<int>(); ia.band_m = s->d_m.as<int>();
   ia.pt_active = nullptr; ia.n_obj = s->n_obj; ia.code_len = s->cfg.code_len; ia.D = s->cfg.num_depth_samples;
   ia.pose_only = pose_only;
+  ia.gather = s->gdev; ia.results = s->d_results.as<float>(); ia.n_bad = s->n_bad;
   ia.mega = mega ? 1 : 0;
   if (mega) {
     ia.tile_base = s->d_tbase_static; ia.tile_rows = kTcRows;
@@ -519,6 +581,7 @@ SolveArgs base_solve(DspgnSolver* s, int pose_only) {
   v.V_count = s->d_V.as<int>(); v.band_m = s->d_m.as<int>();
   v.prm = SolverParams{c.k1, c.k2, c.k3, c.k4, c.b1, c.b2, c.lr, c.s_damp, c.code_len, c.num_depth_samples, c.cut_off, c.sdf_only};
   v.n_obj = s->n_obj; v.pose_only = pose_only; v.results = s->d_results.as<float>();
+  v.gather = s->gdev;
   v.dbg_obj = -1; v.dbg_H = nullptr; v.dbg_b = nullptr; v.dbg_dx = nullptr; v.dbg_loss = nullptr;
   v.dbg_clk = s->clk_on ? s->d_clk.as<long long>() + kClkTiles * kTcMaxSteps * kClkSlots : nullptr;
   return v;
@@ -526,7 +589,8 @@ SolveArgs base_solve(DspgnSolver* s, int pose_only) {
 
 }  // namespace
 
-int dspgn_run_batch(DspgnSolver* s, int mode) {
+namespace {
+int run_batch_impl(DspgnSolver* s, int mode) {
   if (!s) return fail(DSPGN_E_ARG, "null solver");
   if (s->n_obj < 1) return fail(DSPGN_E_ARG, "no batch uploaded");
   if (mode != 0 && mode != 1) return fail(DSPGN_E_ARG, "mode must be 0 or 1");
@@ -591,6 +655,174 @@ int dspgn_run_batch(DspgnSolver* s, int mode) {
   return 0;
 }
 
+GatherDev gather_dev(DspgnSolver* s, int seq) {
+  DspgnSolver::Gather& G = s->gather;
+  GatherDev g{};
+  g.slots = reinterpret_cast<float*>(G.base) + (size_t)(seq & 1) * G.n_slots * DSPGN_RESULT_FLOATS;
+  g.slot_of = G.d_slot_of.as<int>();
+  g.flags = reinterpret_cast<int*>(G.base + G.off_flags);
+  g.ack = reinterpret_cast<int*>(G.base + G.off_ack);
+  g.err = G.d_local.as<int>();
+  g.wait_ns = reinterpret_cast<long long*>(G.d_local.as<unsigned char>() + 8);
+  g.rank = G.rank; g.world = G.world; g.seq = seq;
+  return g;
+}
+
+int gather_layout(DspgnSolver* s, int n_slots, int world, int rank) {
+  DspgnSolver::Gather& G = s->gather;
+  G.n_slots = n_slots; G.world = world; G.rank = rank;
+  const size_t slot_bytes = 2 * (size_t)n_slots * DSPGN_RESULT_FLOATS * 4;
+  G.off_flags = (slot_bytes + 255) / 256 * 256;
+  G.off_ack = G.off_flags + 4 * (size_t)((world + 63) / 64 * 64);
+  if (G.d_local.reserve(64)) return fail(DSPGN_E_ALLOC, "cudaMalloc");
+  CU(cudaMemset(G.d_local.p, 0, 64));
+  return 0;
+}
+}  // namespace
+
+int dspgn_run_batch(DspgnSolver* s, int mode) {
+  if (s) s->gdev = GatherDev{};
+  return run_batch_impl(s, mode);
+}
+
+// ---- multi-GPU result exchange ----------------------------------------------------------------------------------
+int dspgn_gather_create(DspgnSolver* s, int n_slots, int world, DspgnIpcHandle* handle_out) {
+  if (!s || !handle_out || n_slots < 1 || world < 1 || world > 1024) return fail(DSPGN_E_ARG, "bad gather arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= DSPGN_IPC_HANDLE_BYTES, "IPC handle size");
+  CU(cudaSetDevice(s->device));
+  dspgn_gather_close(s);
+  if (int rc = gather_layout(s, n_slots, world, 0)) return rc;
+  DspgnSolver::Gather& G = s->gather;
+  const size_t bytes = G.off_ack + 256;
+  void* p = nullptr;
+  CU(cudaMalloc(&p, bytes));           // plain cudaMalloc: exportable through cudaIpcGetMemHandle
+  G.base = reinterpret_cast<unsigned char*>(p); G.owner = true;
+  CU(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  memset(handle_out, 0, sizeof(*handle_out));
+  if (world > 1) {
+    CU(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle_out->bytes, &h, sizeof(h));
+  }
+  G.active = true;
+  return 0;
+}
+
+int dspgn_gather_open(DspgnSolver* s, const DspgnIpcHandle* handle, int n_slots, int world, int rank) {
+  if (!s || !handle || n_slots < 1 || world < 2 || rank < 1 || rank >= world) return fail(DSPGN_E_ARG, "bad gather arguments");
+  CU(cudaSetDevice(s->device));
+  dspgn_gather_close(s);
+  if (int rc = gather_layout(s, n_slots, world, rank)) return rc;
+  DspgnSolver::Gather& G = s->gather;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle->bytes, sizeof(h));
+  void* p = nullptr;
+  CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));   // rank 0's HBM, reachable over NVLink
+  G.base = reinterpret_cast<unsigned char*>(p); G.owner = false;
+  G.active = true;
+  return 0;
+}
+
+void dspgn_gather_close(DspgnSolver* s) {
+  if (!s) return;
+  DspgnSolver::Gather& G = s->gather;
+  if (G.base) {
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    if (G.owner) cudaFree(G.base); else cudaIpcCloseMemHandle(G.base);
+    cudaGetLastError();
+  }
+  G.base = nullptr; G.active = false; G.owner = false; G.bound_n = -1;
+  G.d_slot_of.release(); G.d_local.release(); G.h_out.release();
+  s->gdev = GatherDev{};
+}
+
+int dspgn_gather_bind(DspgnSolver* s, const int32_t* slots, int n) {
+  if (!s || n < 0 || (n > 0 && !slots)) return fail(DSPGN_E_ARG, "bad argument");
+  DspgnSolver::Gather& G = s->gather;
+  if (!G.active) return fail(DSPGN_E_ARG, "no gather buffer (dspgn_gather_create / dspgn_gather_open first)");
+  if (n > 0 && n != s->n_obj) return fail(DSPGN_E_ARG, "gather_bind: n must equal the resident batch size");
+  for (int i = 0; i < n; ++i)
+    if (slots[i] < 0 || slots[i] >= G.n_slots) return fail(DSPGN_E_ARG, "gather_bind: slot out of range");
+  CU(cudaSetDevice(s->device));
+  if (n > 0) {
+    if (G.d_slot_of.cap < 4 * (size_t)n) CU(cudaStreamSynchronize(s->stream));
+    if (G.d_slot_of.reserve(4 * (size_t)n)) return fail(DSPGN_E_ALLOC, "cudaMalloc");
+    CU(cudaMemcpyAsync(G.d_slot_of.p, slots, 4 * (size_t)n, cudaMemcpyHostToDevice, s->stream));   // pageable source: returns after staging
+  }
+  G.bound_n = n;
+  return 0;
+}
+
+int dspgn_run_batch_gather(DspgnSolver* s, int mode, int seq) {
+  if (!s || seq < 1) return fail(DSPGN_E_ARG, "bad argument");
+  DspgnSolver::Gather& G = s->gather;
+  if (!G.active || G.bound_n < 0) return fail(DSPGN_E_ARG, "gather not bound for the resident batch");
+  CU(cudaSetDevice(s->device));
+  const GatherDev g = gather_dev(s, seq);
+  if (G.bound_n > 0) {
+    s->gdev = g;
+    const int rc = run_batch_impl(s, mode);
+    s->gdev = GatherDev{};
+    if (rc) return rc;
+  }
+  k_gather_publish<<<1, 32, 0, s->stream>>>(g, G.bound_n == 0 ? 1 : 0);
+  if (G.rank == 0) k_gather_wait<<<1, 32 * ((G.world + 31) / 32), 0, s->stream>>>(g);
+  s->ctr.kernel_launches += (G.rank == 0) ? 2 : 1;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+const float* dspgn_gather_device(DspgnSolver* s, int seq) {
+  if (!s || !s->gather.active) return nullptr;
+  return reinterpret_cast<const float*>(s->gather.base) + (size_t)(seq & 1) * s->gather.n_slots * DSPGN_RESULT_FLOATS;
+}
+
+int dspgn_gather_results(DspgnSolver* s, int seq, int n, DspgnObjectOut* out) {
+  if (!s || !out || n < 1) return fail(DSPGN_E_ARG, "bad argument");
+  DspgnSolver::Gather& G = s->gather;
+  if (!G.active || G.rank != 0 || n > G.n_slots) return fail(DSPGN_E_ARG, "gather_results: rank 0 only, n <= n_slots");
+  CU(cudaSetDevice(s->device));
+  const size_t bytes = sizeof(DspgnObjectOut) * (size_t)n;
+  if (G.h_out.reserve(bytes + 64)) return fail(DSPGN_E_ALLOC, "cudaMallocHost");
+  CU(cudaMemcpyAsync(G.h_out.p, dspgn_gather_device(s, seq), bytes, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaMemcpyAsync(G.h_out.as<unsigned char>() + bytes, G.d_local.p, 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  memcpy(out, G.h_out.p, bytes);
+  int err = 0;
+  memcpy(&err, G.h_out.as<unsigned char>() + bytes, 4);
+  if (err) { cudaMemset(G.d_local.p, 0, 4); return fail(DSPGN_E_PEER, "a rank did not publish its results within the timeout"); }
+  return 0;
+}
+
+long long dspgn_gather_wait_ns(DspgnSolver* s) {
+  if (!s || !s->gather.active) return -1;
+  long long v[2] = {0, 0};
+  cudaSetDevice(s->device);
+  if (cudaStreamSynchronize(s->stream) != cudaSuccess) return -1;
+  if (cudaMemcpy(v, s->gather.d_local.p, 16, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return v[1];
+}
+
+__global__ void k_debug_exp(const float* x, int n, int sim3, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) exp_sim3_dev(x + 7 * i, sim3 != 0, out + 12 * i);
+}
+
+int dspgn_debug_exp(int device, int sim3, const float* x, int n, float* out) {
+  if (!x || !out || n < 1) return fail(DSPGN_E_ARG, "bad argument");
+  CU(cudaSetDevice(device));
+  DevBuf dx, dout;
+  if (dx.reserve(28 * (size_t)n) || dout.reserve(48 * (size_t)n)) return fail(DSPGN_E_ALLOC, "cudaMalloc");
+  CU(cudaMemcpy(dx.p, x, 28 * (size_t)n, cudaMemcpyHostToDevice));
+  k_debug_exp<<<(n + 63) / 64, 64>>>(dx.as<float>(), n, sim3, dout.as<float>());
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, 48 * (size_t)n, cudaMemcpyDeviceToHost);
+  dx.release(); dout.release();
+  if (e != cudaSuccess) return fail(DSPGN_E_CUDA, std::string("debug_exp: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 const float* dspgn_results_device(DspgnSolver* s) { return s ? s->d_results.as<float>() : nullptr; }
 
 int dspgn_results(DspgnSolver* s, DspgnObjectOut* out) {
@@ -615,18 +847,28 @@ int dspgn_results(DspgnSolver* s, DspgnObjectOut* out) {
 }
 
 int dspgn_reconstruct_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, DspgnObjectOut* out) {
-  if (int rc = dspgn_upload_batch(s, n_obj, in)) return rc;
-  if (int rc = dspgn_run_batch(s, 0)) return rc;
-  return dspgn_results(s, out);
+  if (!s || !in || !out || n_obj < 1) return fail(DSPGN_E_ARG, "bad argument");
+  // any number of objects: resident batches of at most kMaxObjScan, one after the other
+  for (int o0 = 0; o0 < n_obj; o0 += kMaxObjScan) {
+    const int n = std::min(kMaxObjScan, n_obj - o0);
+    if (int rc = dspgn_upload_batch(s, n, in + o0)) return rc;
+    if (int rc = dspgn_run_batch(s, 0)) return rc;
+    if (int rc = dspgn_results(s, out + o0)) return rc;
+  }
+  return 0;
 }
 
 int dspgn_estimate_pose_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, DspgnObjectOut* out) {
-  if (!s || !in) return fail(DSPGN_E_ARG, "null argument");
+  if (!s || !in || !out || n_obj < 1) return fail(DSPGN_E_ARG, "bad argument");
   for (int o = 0; o < n_obj; ++o)
     if (!in[o].code || !(in[o].scale > 0.f)) return fail(DSPGN_E_ARG, "estimate_pose needs a code and a positive scale per object");
-  if (int rc = dspgn_upload_batch(s, n_obj, in)) return rc;
-  if (int rc = dspgn_run_batch(s, 1)) return rc;
-  return dspgn_results(s, out);
+  for (int o0 = 0; o0 < n_obj; o0 += kMaxObjScan) {
+    const int n = std::min(kMaxObjScan, n_obj - o0);
+    if (int rc = dspgn_upload_batch(s, n, in + o0)) return rc;
+    if (int rc = dspgn_run_batch(s, 1)) return rc;
+    if (int rc = dspgn_results(s, out + o0)) return rc;
+  }
+  return 0;
 }
 
 int dspgn_decode_sdf(DspgnSolver* s, int class_id, const float* code, const float* x, int n, int x_rs, int x_cs,
@@ -638,10 +880,11 @@ int dspgn_decode_sdf(DspgnSolver* s, int class_id, const float* code, const floa
   in.pts = x; in.n_pts = n; in.pts_rs = x_rs; in.pts_cs = x_cs;
   in.rays = nullptr; in.n_rays = 0; in.depth = nullptr; in.n_depth = 0;
   in.code = code; in.scale = 1.f; in.class_id = class_id;
-  if (int rc = dspgn_upload_batch(s, 1, &in)) return rc;
+  if (int rc = upload_batch_impl(s, 1, &in, true)) return rc;      // forward only: no J^T J partial / band buffers
   if (s->d_sdf.reserve(4 * (size_t)n)) return fail(DSPGN_E_ALLOC, "cudaMalloc");
   s->ctr = DspgnCounters{};
   s->ev_used = 0;
+  s->gdev = GatherDev{};
   if (int rc = launch_init(s, 0)) return rc;
   TermArgs a = base_term(s, MODE_PTSFWD);
   if (int rc = launch_term(s, a, n)) return rc;
@@ -653,8 +896,14 @@ int dspgn_decode_sdf(DspgnSolver* s, int class_id, const float* code, const floa
 
 int dspgn_debug_system(DspgnSolver* s, int obj, int mode, float* H, float* b, float* dx, float* J_rows,
                        float* res_rows, float* losses) {
+  return dspgn_debug_system_iter(s, obj, mode, 0, H, b, dx, J_rows, res_rows, losses);
+}
+
+int dspgn_debug_system_iter(DspgnSolver* s, int obj, int mode, int iter, float* H, float* b, float* dx, float* J_rows,
+                            float* res_rows, float* losses) {
   if (!s || !H || !b || !dx) return fail(DSPGN_E_ARG, "null argument");
   if (obj < 0 || obj >= s->n_obj) return fail(DSPGN_E_ARG, "bad object index");
+  if (iter < 0 || iter > 1000) return fail(DSPGN_E_ARG, "bad iteration index");
   CU(cudaSetDevice(s->device));
   const int pose_only = mode;
   const int P = pose_only ? 6 : 7 + s->cfg.code_len;
@@ -665,13 +914,22 @@ int dspgn_debug_system(DspgnSolver* s, int obj, int mode, float* H, float* b, fl
   float* dres = dJp + (size_t)npts * P;
   s->ctr = DspgnCounters{};
   s->ev_used = 0;
+  s->gdev = GatherDev{};
   int rc = launch_init(s, pose_only);
-  if (!rc) rc = launch_terms(s, pose_only, dJp, dres, obj);
+  for (int e = 0; e < iter && !rc; ++e) {            // advance the whole batch `iter` GN iterations (per-iteration schedule)
+    rc = launch_terms(s, pose_only, nullptr, nullptr, -1, e);
+    if (rc) break;
+    SolveArgs v = base_solve(s, pose_only);
+    v.last_iter = 0; v.iter_index = e;
+    k_solve<<<s->n_obj, kSolveThreads, 0, s->stream>>>(v);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(DSPGN_E_CUDA, "k_solve launch failed");
+  }
+  if (!rc) rc = launch_terms(s, pose_only, dJp, dres, obj, iter);
   if (!rc) {
     SolveArgs v = base_solve(s, pose_only);
     float* d = s->d_dbg.as<float>();
     v.dbg_obj = obj; v.dbg_H = d; v.dbg_b = d + kPMax * kPMax; v.dbg_dx = v.dbg_b + kPMax; v.dbg_loss = v.dbg_dx + kPMax;
-    v.last_iter = 0; v.iter_index = 0;
+    v.last_iter = 0; v.iter_index = iter;
     cudaMemsetAsync(d, 0, 4 * ((size_t)kPMax * kPMax + 2 * kPMax + 8), s->stream);
     k_solve<<<s->n_obj, kSolveThreads, 0, s->stream>>>(v);
     if (cudaGetLastError() != cudaSuccess) rc = fail(DSPGN_E_CUDA, "k_solve launch failed");

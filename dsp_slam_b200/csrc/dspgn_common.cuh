@@ -24,6 +24,7 @@ struct ObjMeta {
   int class_id;
   float scale;                 // estimate_pose only
   int has_code;
+  int bad;                     // unusable detection, rejected at upload: status DSPGN_ST_BAD_INPUT, never evaluated
 };
 
 // Evolving per-object GN state (device resident for all iterations).

@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decoder_simt(TermArgs a) {
     }
     __syncthreads();
     if (a.dbg_J != nullptr && o == a.dbg_obj && a.mode == MODE_SDF) {
-      const int P = a.dbg_P, npose = P - L;
+      const int P = a.dbg_P, npose = a.pose_only ? 6 : 7;
       for (int idx = tid; idx < nrows * P; idx += kThreads) {
         const int p = idx / P, c = idx - p * P;
         const int ci = (c < npose) ? (kMaxCode + c) : (c - npose);

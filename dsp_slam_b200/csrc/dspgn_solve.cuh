@@ -7,6 +7,107 @@
 
 namespace dspgn {
 
+template <class T>
+__device__ __forceinline__ T ldv(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
+
+// ---- multi-GPU result exchange (include/dspgn.h "Multi-GPU result exchange") ------------------------------
+// All pointers but slot_of point into rank 0's HBM: local memory on rank 0, CUDA-IPC peer mappings (NVLink)
+// on every other rank.
+struct GatherDev {
+  float* slots;          // slot set of this step [n_slots][DSPGN_RESULT_FLOATS]; nullptr = exchange off
+  const int* slot_of;    // [n_obj] slot of each resident object (local memory)
+  int* flags;            // [world] last step each rank has published
+  int* ack;              // last step rank 0 has consumed
+  int* err;              // LOCAL error word: 1 = a wait timed out
+  long long* wait_ns;    // LOCAL: duration of the last wait (rank 0), for the bench's exchange_ms
+  int rank, world, seq;
+};
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;   // soft failure, never a trap
+
+// spin until *p >= need (system scope); false on timeout
+__device__ inline bool wait_ge_sys(const int* p, int need) {
+  const unsigned long long t0 = globaltimer_ns();
+  while (ld_acquire_sys(p) < need) {
+    __nanosleep(200);
+    if (globaltimer_ns() - t0 > kPeerTimeoutNs) return false;
+  }
+  return true;
+}
+
+// flow control at the start of a step: rank 0 acknowledges everything before the previous step as consumed (its
+// stream ran the D2H / consumers of step seq-2 before this kernel); the others make sure the slot set they are
+// about to overwrite (written two steps ago) has been consumed.
+__device__ inline void gather_step_begin(const GatherDev& g) {
+  if (g.slots == nullptr) return;
+  if (g.rank == 0) st_release_sys(g.ack, g.seq - 1);
+  else if (!wait_ge_sys(g.ack, g.seq - 2)) *g.err = 1;
+}
+
+// end of a step (its own launch, stream-ordered behind every kernel that stored records): publish
+__global__ void k_gather_publish(GatherDev g, int with_begin) {
+  if (threadIdx.x != 0) return;
+  if (with_begin) gather_step_begin(g);          // rank without objects this step: no k_init ran
+  __threadfence_system();
+  st_release_sys(g.flags + g.rank, g.seq);
+}
+
+// rank 0: wait until every rank has published step seq
+__global__ void k_gather_wait(GatherDev g) {
+  const int r = threadIdx.x;
+  const unsigned long long t0 = globaltimer_ns();
+  bool ok = true;
+  if (r < g.world) ok = wait_ge_sys(g.flags + r, g.seq);
+  if (!ok) *g.err = 1;
+  __syncwarp();
+  if (r == 0) *g.wait_ns = (long long)(globaltimer_ns() - t0);
+}
+
+// Result record of one object (DspgnObjectOut layout): pose back in camera<-object form (optimizer.py:200 / :83-84),
+// code, loss, status, counters; mirrored into rank 0's gather buffer when the exchange is on.
+__device__ inline void write_record(float* results, const GatherDev& g, int o, const ObjState& st, int pose_only, float scale) {
+  float* r = results + (size_t)o * DSPGN_RESULT_FLOATS;
+  float Toc[12], Tco[12];
+  for (int i = 0; i < 12; ++i) Toc[i] = ldv(&st.T_oc[i]);
+  inv_affine(Toc, Tco, nullptr);                         // optimizer.py:200 / :83
+  if (pose_only) {                                       // optimizer.py:84: t_cam_obj[:3,:3] /= scale
+    for (int i = 0; i < 3; ++i)
+      for (int c = 0; c < 3; ++c) Tco[i * 4 + c] /= scale;
+  }
+  for (int i = 0; i < 12; ++i) r[i] = Tco[i];
+  r[12] = 0.f; r[13] = 0.f; r[14] = 0.f; r[15] = 1.f;
+  for (int i = 0; i < kMaxCode; ++i) r[16 + i] = ldv(&st.z[i]);
+  r[80] = ldv(&st.loss);
+  reinterpret_cast<int*>(r)[81] = ldv(&st.status);
+  reinterpret_cast<int*>(r)[82] = ldv(&st.V);
+  reinterpret_cast<int*>(r)[83] = ldv(&st.m);
+  reinterpret_cast<int*>(r)[84] = ldv(&st.iters);
+  reinterpret_cast<int*>(r)[85] = 0;
+  reinterpret_cast<int*>(r)[86] = 0;
+  reinterpret_cast<int*>(r)[87] = 0;
+  if (g.slots != nullptr) {
+    // multi-GPU: the same record into the object's slot of rank 0's gather buffer.  On ranks > 0 this is a
+    // peer-mapped address: plain st.global that travel over NVLink; they are published by k_gather_publish.
+    float4* dst = reinterpret_cast<float4*>(g.slots + (size_t)g.slot_of[o] * DSPGN_RESULT_FLOATS);
+    const float4* src = reinterpret_cast<const float4*>(r);
+#pragma unroll 2
+    for (int i = 0; i < DSPGN_RESULT_FLOATS / 4; ++i) dst[i] = src[i];
+  }
+}
+
 struct InitArgs {
   const ObjMeta* meta;
   ObjState* state;
@@ -19,10 +120,14 @@ struct InitArgs {
   // persistent-kernel mode: also seed the work queue with every object's iteration-0 tiles
   int mega; const int* tile_base; int tile_rows; int* q_items; int* q_flag; int* q_head; int* q_tail;
   int* tiles_left; int* obj_iter; int* done_objects; int total_tiles0;
+  GatherDev gather;
+  float* results;          // records of objects rejected at upload are written here
+  int n_bad;
 };
 
 __global__ void k_init(InitArgs a) {
   const int o = blockIdx.x, tid = threadIdx.x;
+  if (o == 0 && tid == 0) gather_step_begin(a.gather);
   ObjState& st = a.state[o];
   const ObjMeta M = a.meta[o];
   if (a.pt_active != nullptr)
@@ -37,15 +142,19 @@ __global__ void k_init(InitArgs a) {
         for (int c = 0; c < 3; ++c) Tco[r * 4 + c] *= M.scale;
     inv_affine(Tco, st.T_oc, nullptr);     // optimizer.py:55 / :104
     derive_depth_range(st, a.D);
-    st.loss = 0.f; st.status = 0; st.iters = 0; st.V = 0; st.m = 0; st.n_active = M.n_pts;
+    st.loss = 0.f; st.status = M.bad ? DSPGN_ST_BAD_INPUT : 0; st.iters = 0; st.V = 0; st.m = 0; st.n_active = M.n_pts;
     a.V_count[o] = 0;
     a.band_m[o] = 0;
+  }
+  if (M.bad) {                               // rejected at upload: no tile, no solve -- its record is final now
+    __syncthreads();
+    if (tid == 0) write_record(a.results, a.gather, o, st, a.pose_only, M.scale);
   }
   if (a.mega) {
     const int nt = (M.n_pts + a.tile_rows - 1) / a.tile_rows, base = a.tile_base[o];
     for (int j = tid; j < nt; j += blockDim.x) { a.q_items[base + j] = (o << 16) | j; a.q_flag[base + j] = 1; }
     if (tid == 0) { a.tiles_left[o] = nt; a.obj_iter[o] = 0; }
-    if (o == 0 && tid == 0) { *a.q_head = 0; *a.q_tail = a.total_tiles0; *a.done_objects = 0; }
+    if (o == 0 && tid == 0) { *a.q_head = 0; *a.q_tail = a.total_tiles0; *a.done_objects = a.n_bad; }
   }
 }
 
@@ -66,13 +175,11 @@ struct SolveArgs {
   int last_iter;          // write the result record
   int iter_index;
   float* results;         // [n_obj][DSPGN_RESULT_FLOATS]
+  GatherDev gather;       // optional: the record also goes straight into rank 0's HBM (peer store over NVLink)
   // debug: dump the system of object dbg_obj and do not update any state
   int dbg_obj; float* dbg_H; float* dbg_b; float* dbg_dx; float* dbg_loss;
   long long* dbg_clk;      // optional: 16 clock64 stamps of object 0's CTA
 };
-
-template <class T>
-__device__ __forceinline__ T ldv(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
 
 constexpr int kSolveThreads = 256;
 constexpr int kPMax = 7 + kMaxCode;   // 71
@@ -84,25 +191,8 @@ __device__ __forceinline__ int ext_to_int(int e, int npose, int L) {
   return (e < npose) ? (kMaxCode + e) : (e - npose);
 }
 
-__device__ void write_result(const SolveArgs& a, int o, const ObjState& st) {
-  float* r = a.results + (size_t)o * DSPGN_RESULT_FLOATS;
-  float Toc[12], Tco[12];
-  for (int i = 0; i < 12; ++i) Toc[i] = ldv(&st.T_oc[i]);
-  inv_affine(Toc, Tco, nullptr);                         // optimizer.py:200 / :83
-  if (a.pose_only) {                                     // optimizer.py:84: t_cam_obj[:3,:3] /= scale
-    const float s = a.meta[o].scale;
-    for (int i = 0; i < 3; ++i)
-      for (int c = 0; c < 3; ++c) Tco[i * 4 + c] /= s;
-  }
-  for (int i = 0; i < 12; ++i) r[i] = Tco[i];
-  r[12] = 0.f; r[13] = 0.f; r[14] = 0.f; r[15] = 1.f;
-  for (int i = 0; i < kMaxCode; ++i) r[16 + i] = ldv(&st.z[i]);
-  r[80] = ldv(&st.loss);
-  reinterpret_cast<int*>(r)[81] = ldv(&st.status);
-  reinterpret_cast<int*>(r)[82] = ldv(&st.V);
-  reinterpret_cast<int*>(r)[83] = ldv(&st.m);
-  reinterpret_cast<int*>(r)[84] = ldv(&st.iters);
-  reinterpret_cast<int*>(r)[85] = 0;
+__device__ __forceinline__ void write_result(const SolveArgs& a, int o, const ObjState& st) {
+  write_record(a.results, a.gather, o, st, a.pose_only, a.meta[o].scale);
 }
 
 constexpr int kElimThreads = 96;      // rows 0..70 live in the first three warps

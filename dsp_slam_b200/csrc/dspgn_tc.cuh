@@ -642,7 +642,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
       }
       epi_bar_sync();
       if (a.dbg_J != nullptr && o == a.dbg_obj && a.mode == MODE_SDF) {
-        const int P = a.dbg_P, npose = P - L;
+        const int P = a.dbg_P, npose = a.pose_only ? 6 : 7;
         for (int idx = tid; idx < nrows * P; idx += kTcEpiThreads) {
           const int p = idx / P, c = idx - p * P;
           const int ci = (c < npose) ? (kMaxCode + c) : (c - npose);

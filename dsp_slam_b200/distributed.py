@@ -1,11 +1,28 @@
-"""Object-sharded multi-GPU driver: one process per GPU, no data-path collective, ONE all-gather.
+"""Object-sharded multi-GPU reconstruction: one process per GPU, no data-path collective.
 
 The reference reconstructs objects one at a time on one GPU (src/LocalMapping_util.cc:165-203).  Objects
-are independent GN problems, so a batch is split into contiguous per-rank blocks (after a stable sort
-by decoder class, so a rank touches as few weight sets as possible), every rank runs its block through
-its own solver, and the fixed-size result records (DSPGN_RESULT_FLOATS floats per object: pose, code,
-loss, status, counters) are exchanged with a single all_gather -- NCCL on GPUs, gloo in the CPU tests.
+are independent GN problems, so a batch is split into contiguous per-rank blocks (after a stable sort by
+decoder class, so that a rank touches as few weight sets as possible) and every rank runs its block through
+its own solver.  The only exchange is the fixed-size result record of every object (DSPGN_RESULT_FLOATS
+floats: pose, code, loss, status, counters) going back to rank 0.
+
+Two exchange mechanisms:
+
+* ``peer`` (default on GPUs): rank 0 owns a gather buffer in its HBM and exports it with CUDA IPC; the other
+  ranks map it over NVLink/NVSwitch, and the solve step that finishes an object stores the record straight
+  into rank 0's buffer at the object's ORIGINAL index -- issued from the same kernel that runs the tcgen05
+  tiles.  No collective kernel, no reorder pass; a per-rank sequence flag publishes a finished step
+  (include/dspgn.h "Multi-GPU result exchange").
+* ``nccl`` / gloo: one ``all_gather_into_tensor`` of the padded per-rank record blocks on the solver's stream
+  (every rank gets everything).  Used by the CPU tests (gloo) and as the fallback when CUDA IPC is not
+  available.
+
+Every rank passes the SAME full object list (SPMD, like every torch.distributed program); rank 0 gets the
+results in the original order.
 """
+import ctypes as C
+import sys
+
 import numpy as np
 
 from . import _lib
@@ -26,7 +43,7 @@ def shard_plan(class_ids, world_size):
 
 
 def shard_for_rank(objs, world_size, rank):
-    order, bounds = shard_plan([int(o.get("class_id", 0)) for o in objs], world_size)
+    order, bounds = shard_plan([int(o.get("class_id", 0) or 0) for o in objs], world_size)
     idx = order[bounds[rank]:bounds[rank + 1]]
     return [objs[i] for i in idx], idx
 
@@ -73,31 +90,188 @@ class _DevView:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
 
 
-class ShardedOptimizer:
-    """reconstruct_batch over all ranks of an initialised torch.distributed process group (NCCL).
-    Every rank passes the SAME full object list; every rank gets all results back."""
+class PeerGather:
+    """The library-level exchange of one solver: rank 0's gather buffer, mapped by every other rank."""
 
-    def __init__(self, optimizer, group=None):
+    def __init__(self, solver, world, rank, capacity, group=None):
+        import torch.distributed as dist
+        lib = _lib.load()
+        self.solver, self.world, self.rank, self.capacity = solver, world, rank, int(capacity)
+        self.seq = 0
+        h = _lib.IpcHandle()
+        payload = [None]
+        if rank == 0:
+            _lib.check(lib.dspgn_gather_create(solver.handle, self.capacity, world, C.byref(h)))
+            payload = [bytes(h.bytes)]
+        if world > 1:
+            dist.broadcast_object_list(payload, src=0, group=group)
+            if rank != 0:
+                C.memmove(h.bytes, payload[0], _lib.IPC_HANDLE_BYTES)
+                _lib.check(lib.dspgn_gather_open(solver.handle, C.byref(h), self.capacity, world, rank))
+
+    def bind(self, slots):
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        _lib.check(_lib.load().dspgn_gather_bind(self.solver.handle, slots.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                 int(slots.shape[0])))
+
+    def run(self, mode=0):
+        """All GN iterations of the resident shard; records land in rank 0's HBM; publish (async)."""
+        self.seq += 1
+        _lib.check(_lib.load().dspgn_run_batch_gather(self.solver.handle, mode, self.seq))
+        return self.seq
+
+    def results(self, n):
+        """rank 0: wait for every rank's flag, D2H of the first n slots -> (n, RESULT_FLOATS) float32."""
+        out = (_lib.ObjectOut * n)()
+        _lib.check(_lib.load().dspgn_gather_results(self.solver.handle, self.seq, n, out))
+        return np.frombuffer(out, dtype=np.float32, count=n * RESULT_FLOATS).reshape(n, RESULT_FLOATS).copy()
+
+    def device_ptr(self):
+        return _lib.load().dspgn_gather_device(self.solver.handle, self.seq)
+
+    def wait_ms(self):
+        return _lib.load().dspgn_gather_wait_ns(self.solver.handle) * 1e-6
+
+    def close(self):
+        _lib.load().dspgn_gather_close(self.solver.handle)
+
+
+class ShardedOptimizer:
+    """`reconstruct_batch` over all ranks of an initialised torch.distributed process group.
+
+    Every rank passes the SAME full object list.  Rank 0 returns the list of results in the original order;
+    the other ranks return None (``all_ranks=True``: the records are broadcast and every rank returns them).
+    exchange: "peer" (NVLink peer stores from the solve kernel, no collective), "nccl" (all-gather on the
+    solver stream) or "auto" (= peer, falling back to nccl when the CUDA-IPC mapping cannot be set up)."""
+
+    def __init__(self, optimizer, group=None, exchange="auto", capacity=4096):
         import torch.distributed as dist
         self.opt = optimizer
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.exchange = "nccl"
+        self.peer = None
+        self.capacity = capacity
+        if exchange in ("auto", "peer"):
+            ok = [1]
+            try:
+                self.peer = PeerGather(optimizer.solver, self.world, self.rank, capacity, group)
+            except _lib.DspgnError as e:
+                if exchange == "peer":
+                    raise
+                print(f"[dsp_slam_b200] peer exchange unavailable on rank {self.rank} ({e}); using NCCL all-gather",
+                      file=sys.stderr)
+                ok = [0]
+            if self.world > 1:                    # all ranks must agree on the mechanism
+                import torch
+                dev = torch.device("cuda", optimizer.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+                t = torch.tensor(ok, dtype=torch.int32, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+                ok = [int(t.item())]
+            if ok[0]:
+                self.exchange = "peer"
+            elif self.peer is not None:
+                self.peer.close()
+                self.peer = None
 
-    def reconstruct_batch(self, objs):
+    # -- the three phases, for callers that keep the shard resident (bench.py's device-timed loop) ----------
+    def plan(self, objs):
+        order, bounds = shard_plan([int(o.get("class_id", 0) or 0) for o in objs], self.world)
+        idx = order[bounds[self.rank]:bounds[self.rank + 1]]
+        return order, bounds, idx
+
+    def upload_shard(self, objs):
+        """Pack + H2D of this rank's block of the full list; binds the objects' original indices as slots."""
+        if len(objs) > self.capacity:
+            raise ValueError(f"batch of {len(objs)} objects exceeds the gather capacity {self.capacity}")
+        self._order, self._bounds, idx = self.plan(objs)
+        self._n_total = len(objs)
+        self._idx = idx
+        if len(idx):
+            self.opt.solver.upload([objs[i] for i in idx])
+        if self.peer is not None:
+            self.peer.bind(idx)
+
+    def run_shard(self, mode=0):
+        """Enqueue all GN iterations of the resident shard plus, with the peer mechanism, the exchange
+        (records stored into rank 0's HBM by the solve step, flag published; rank 0 also waits) -- asynchronous."""
+        if self.peer is not None:
+            return self.peer.run(mode)
+        if len(self._idx):
+            self.opt.solver.run(mode)
+        return None
+
+    def _is_cpu_group(self):
+        import torch.distributed as dist
+        return dist.get_backend(self.group) == "gloo"
+
+    def exchange_async_nccl(self):
+        """nccl mechanism, device side only: all-gather of the padded per-rank record blocks on the current
+        stream (the bench's timed loop); returns the gathered (world, max_n, RESULT_FLOATS) tensor."""
         import torch
-        n = len(objs)
-        order, bounds = shard_plan([int(o.get("class_id", 0)) for o in objs], self.world)
-        mine = [objs[i] for i in order[bounds[self.rank]:bounds[self.rank + 1]]]
+        import torch.distributed as dist
         dev = torch.device("cuda", self.opt.device)
-        if mine:
-            s = self.opt.solver
-            s.set_stream(torch.cuda.current_stream(dev).cuda_stream)
-            s.upload(mine)
-            s.run(0)
-            local = torch.as_tensor(_DevView(s.results_device_ptr(), len(mine) * RESULT_FLOATS), device=dev)
-            local = local.view(len(mine), RESULT_FLOATS)
+        k, max_n = len(self._idx), int(np.max(np.diff(self._bounds)))
+        if getattr(self, "_pad", None) is None or self._pad.shape[0] != max_n:
+            self._pad = torch.zeros((max_n, RESULT_FLOATS), dtype=torch.float32, device=dev)
+            self._gath = torch.empty((self.world * max_n, RESULT_FLOATS), dtype=torch.float32, device=dev)
+        if k:
+            local = torch.as_tensor(_DevView(self.opt.solver.results_device_ptr(), k * RESULT_FLOATS), device=dev)
+            self._pad[:k].copy_(local.view(k, RESULT_FLOATS))
+        dist.all_gather_into_tensor(self._gath, self._pad, group=self.group)
+        return self._gath.view(self.world, max_n, RESULT_FLOATS)
+
+    def gather_records(self):
+        """peer: rank 0 -> (n_total, RESULT_FLOATS) numpy, others -> None.  nccl: every rank gets the array."""
+        n = self._n_total
+        if self.peer is not None:
+            if self.rank == 0:
+                return self.peer.results(n)
+            self.opt.solver.synchronize()
+            return None
+        import torch
+        s = self.opt.solver
+        k = len(self._idx)
+        if self._is_cpu_group():
+            # gloo process group (CPU collective): records come down first, then the all-gather
+            if k:
+                raw = s.results_raw()
+                local = torch.from_numpy(np.frombuffer(raw, dtype=np.float32, count=k * RESULT_FLOATS)
+                                         .reshape(k, RESULT_FLOATS).copy())
+            else:
+                local = torch.zeros((0, RESULT_FLOATS), dtype=torch.float32)
         else:
-            local = torch.zeros((0, RESULT_FLOATS), dtype=torch.float32, device=dev)
-        rec = all_gather_records(local, n, self.world, self.rank, order, bounds, self.group)
-        return records_to_results(rec.cpu().numpy(), self.opt.code_len)
+            dev = torch.device("cuda", self.opt.device)
+            if k:
+                local = torch.as_tensor(_DevView(s.results_device_ptr(), k * RESULT_FLOATS), device=dev).view(k, RESULT_FLOATS)
+            else:
+                local = torch.zeros((0, RESULT_FLOATS), dtype=torch.float32, device=dev)
+        rec = all_gather_records(local, n, self.world, self.rank, self._order, self._bounds, self.group)
+        return rec.cpu().numpy()
+
+    # -- whole call ------------------------------------------------------------------------------------------
+    def reconstruct_batch(self, objs, all_ranks=False):
+        import torch
+        cpu_group = self.peer is None and self._is_cpu_group()
+        dev = torch.device("cpu") if cpu_group else torch.device("cuda", self.opt.device)
+        if self.peer is None and not cpu_group:
+            self.opt.solver.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        self.upload_shard(objs)
+        self.run_shard(0)
+        rec = self.gather_records()
+        if all_ranks and self.peer is not None and self.world > 1:
+            import torch.distributed as dist
+            t = torch.empty((len(objs), RESULT_FLOATS), dtype=torch.float32, device=dev)
+            if self.rank == 0:
+                t.copy_(torch.from_numpy(rec))
+            dist.broadcast(t, src=0, group=self.group)
+            rec = t.cpu().numpy()
+        if rec is None:
+            return None
+        return records_to_results(rec, self.opt.code_len)
+
+    def close(self):
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None

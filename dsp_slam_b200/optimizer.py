@@ -16,6 +16,8 @@ objects of a keyframe).  Never raises for per-object failures: those come back a
 (optimizer.py:130-150); only misuse / missing GPU raise.
 """
 import ctypes as C
+import sys
+
 import numpy as np
 
 from . import _lib
@@ -51,6 +53,15 @@ def _cfg_has(node, key):
 
 
 _FP = C.POINTER(C.c_float)
+_warned = set()
+
+
+def _warn_once(key, msg):
+    """The embedded interpreter has no exception handler above us (an uncaught Python exception in the
+    LocalMapping std::thread is std::terminate): failures are reported on stderr, once per kind."""
+    if key not in _warned:
+        _warned.add(key)
+        print(f"[dsp_slam_b200] {msg}", file=sys.stderr, flush=True)
 
 
 def _f32(a):
@@ -137,8 +148,8 @@ class BatchSolver:
             Cd = o.get("code")
             if Cd is not None:
                 Cd = np.ascontiguousarray(Cd, dtype=np.float32).reshape(-1)
-                if Cd.shape[0] < code_len:
-                    raise ValueError("code shorter than code_len")
+                if Cd.shape[0] < code_len:                 # zero-pad (optimizer.py:97-100 slices code[:code_len])
+                    Cd = np.concatenate([Cd, np.zeros(code_len - Cd.shape[0], np.float32)])
                 rec["code"][i] = Cd.ctypes.data
                 keep.append(Cd)
             sc = o.get("scale")
@@ -159,6 +170,9 @@ class BatchSolver:
 
     def run(self, mode=0):
         _lib.check(_lib.load().dspgn_run_batch(self.handle, mode))
+
+    def synchronize(self):
+        _lib.check(_lib.load().dspgn_solver_sync(self.handle))
 
     def results_raw(self):
         out = (_lib.ObjectOut * self.n_obj)()
@@ -200,14 +214,14 @@ class BatchSolver:
                                                 out.ctypes.data_as(_FP)))
         return out
 
-    def debug_system(self, obj=0, mode=0, want_rows=False, n_pts=0):
+    def debug_system(self, obj=0, mode=0, want_rows=False, n_pts=0, iteration=0):
         P = 6 if mode else 7 + self.cfg.code_len
         H = np.zeros((P, P), np.float32); b = np.zeros(P, np.float32); dx = np.zeros(P, np.float32)
         losses = np.zeros(4, np.float32)
         J = np.zeros((n_pts, P), np.float32) if want_rows else None
         r = np.zeros(n_pts, np.float32) if want_rows else None
-        _lib.check(_lib.load().dspgn_debug_system(
-            self.handle, obj, mode, H.ctypes.data_as(_FP), b.ctypes.data_as(_FP), dx.ctypes.data_as(_FP),
+        _lib.check(_lib.load().dspgn_debug_system_iter(
+            self.handle, obj, mode, int(iteration), H.ctypes.data_as(_FP), b.ctypes.data_as(_FP), dx.ctypes.data_as(_FP),
             J.ctypes.data_as(_FP) if want_rows else None, r.ctypes.data_as(_FP) if want_rows else None,
             losses.ctypes.data_as(_FP)))
         return dict(H=H, b=b, dx=dx, J=J, res=r, sdf_loss=losses[0], render_loss=losses[1],
@@ -283,28 +297,72 @@ class Optimizer(object):
         self.solver = BatchSolver(self._dev_decoders, c, device)
 
     # -- reference surface --------------------------------------------------------------------
+    # These three are called from C++ through pybind11 with no handler above them
+    # (src/LocalMapping_util.cc:109-110,179-196,390-428): they NEVER raise.  Anything that goes wrong --
+    # malformed arrays, an unusable detection, a CUDA error -- comes back as the reference's soft failure
+    # (optimizer.py:131,136,143,150: is_good=False, t_cam_obj=None, code=None) with one line on stderr.
+    @staticmethod
+    def _failed(status=-1, loss=0.0):
+        return ResultDict(t_cam_obj=None, code=None, is_good=False, loss=float(loss), status=status)
+
     def reconstruct_object(self, t_cam_obj, pts, rays, depth, code=None):
         """optimizer.py:88-203.  Returns ResultDict(t_cam_obj (4,4) f32 | None, code (L,) f32 | None,
         is_good, loss)."""
-        out = self.solver.reconstruct([dict(t_cam_obj=t_cam_obj, pts=pts, rays=rays, depth=depth,
-                                            code=None if code is None else np.asarray(code)[:self.code_len])])
-        return _unpack_all(out, 1, self.code_len)[0]
+        try:
+            out = self.solver.reconstruct([dict(t_cam_obj=t_cam_obj, pts=pts, rays=rays, depth=depth,
+                                                code=None if code is None else np.asarray(code)[:self.code_len])])
+            return _unpack_all(out, 1, self.code_len)[0]
+        except Exception as e:            # noqa: BLE001 -- see the comment above
+            _warn_once(("reconstruct_object", type(e).__name__), f"reconstruct_object failed softly: {e!r}")
+            return self._failed()
 
     def estimate_pose_cam_obj(self, t_co_se3, scale, pts, code):
-        """optimizer.py:45-86.  Returns the optimised SE(3) object->camera transform, (4,4) f32."""
-        out = self.solver.estimate_pose([dict(t_cam_obj=t_co_se3, pts=pts, code=np.asarray(code)[:self.code_len],
-                                              scale=float(scale))])
-        return np.array(out[0].t_cam_obj[:], dtype=np.float32).reshape(4, 4)
+        """optimizer.py:45-86.  Returns the optimised SE(3) object->camera transform, (4,4) f32.
+        The C++ caller casts the return value to Eigen::Matrix4f unconditionally
+        (src/LocalMapping_util.cc:109-110), so a failed optimisation (non-finite residuals, singular system,
+        unusable input) returns the INPUT pose unchanged (logged once) instead of garbage or an exception."""
+        try:
+            T0 = np.array(t_co_se3, dtype=np.float32).reshape(4, 4)
+        except Exception as e:            # noqa: BLE001
+            _warn_once(("estimate_pose", "input"), f"estimate_pose_cam_obj: unusable pose argument: {e!r}")
+            return np.eye(4, dtype=np.float32)
+        try:
+            out = self.solver.estimate_pose([dict(t_cam_obj=t_co_se3, pts=pts, code=np.asarray(code)[:self.code_len],
+                                                  scale=float(scale))])
+            if int(out[0].status) != _lib.ST_OK:
+                _warn_once(("estimate_pose", int(out[0].status)),
+                           f"estimate_pose_cam_obj: soft failure (status {int(out[0].status)}), input pose kept")
+                return T0
+            return np.array(out[0].t_cam_obj[:], dtype=np.float32).reshape(4, 4)
+        except Exception as e:            # noqa: BLE001
+            _warn_once(("estimate_pose", type(e).__name__), f"estimate_pose_cam_obj failed softly: {e!r}")
+            return T0
 
     # -- batched extension ----------------------------------------------------------------------
-    def reconstruct_batch(self, objs):
-        """objs: list of dicts(t_cam_obj, pts, rays, depth, [code], [class_id]) -> list of ResultDict."""
-        out = self.solver.reconstruct(objs)
-        return _unpack_all(out, len(objs), self.code_len)
+    def reconstruct_batch(self, objs, strict=True):
+        """objs: list of dicts(t_cam_obj, pts, rays, depth, [code], [class_id]) -> list of ResultDict.
+        Any number of objects (the library walks resident batches of 1024).  Per-object problems are
+        per-object soft failures; strict=False additionally turns call-level errors into all-failed results."""
+        try:
+            out = self.solver.reconstruct(objs)
+            return _unpack_all(out, len(objs), self.code_len)
+        except Exception as e:            # noqa: BLE001
+            if strict:
+                raise
+            _warn_once(("reconstruct_batch", type(e).__name__), f"reconstruct_batch failed softly: {e!r}")
+            return [self._failed() for _ in objs]
 
-    def estimate_pose_batch(self, objs):
+    def estimate_pose_batch(self, objs, return_status=False):
+        """Batched estimate_pose_cam_obj.  Failed objects keep their input pose; return_status=True also returns
+        the per-object DSPGN_ST_* codes so that a native caller can skip them."""
         out = self.solver.estimate_pose(objs)
-        return [np.array(out[i].t_cam_obj[:], dtype=np.float32).reshape(4, 4) for i in range(len(objs))]
+        Ts, st = [], []
+        for i, o in enumerate(objs):
+            s = int(out[i].status)
+            st.append(s)
+            Ts.append(np.array(out[i].t_cam_obj[:], dtype=np.float32).reshape(4, 4) if s == _lib.ST_OK
+                      else np.array(o["t_cam_obj"], dtype=np.float32).reshape(4, 4))
+        return (Ts, st) if return_status else Ts
 
 
 def create_voxel_grid(vol_dim=128):
@@ -352,14 +410,18 @@ class MeshExtractor(object):
         """optimizer.py:214-223.  Marching cubes by scikit-image exactly like the reference when it is installed
         (DSP-SLAM's own environment); otherwise the dependency-free marching-tetrahedra fallback of
         dsp_slam_b200.mesh (same level set, different triangulation)."""
-        sdf = self.sdf_grid(code)
-        voxel_size = 2.0 / (self.voxels_dim - 1)
         try:
-            from skimage import measure
-            mc = getattr(measure, "marching_cubes_lewiner", None) or measure.marching_cubes
-            verts, faces, _, _ = mc(sdf, level=0.0, spacing=[voxel_size] * 3)
-        except ImportError:
-            from .mesh import marching_tetrahedra
-            verts, faces = marching_tetrahedra(sdf, level=0.0, spacing=[voxel_size] * 3)
-        verts = verts + np.array([-1.0, -1.0, -1.0])          # reconstruct/utils.py:131-137
-        return ResultDict(vertices=verts.astype("float32"), faces=faces.astype("int32"))
+            sdf = self.sdf_grid(code)
+            voxel_size = 2.0 / (self.voxels_dim - 1)
+            try:
+                from skimage import measure
+                mc = getattr(measure, "marching_cubes_lewiner", None) or measure.marching_cubes
+                verts, faces, _, _ = mc(sdf, level=0.0, spacing=[voxel_size] * 3)
+            except ImportError:
+                from .mesh import marching_tetrahedra
+                verts, faces = marching_tetrahedra(sdf, level=0.0, spacing=[voxel_size] * 3)
+            verts = verts + np.array([-1.0, -1.0, -1.0])          # reconstruct/utils.py:131-137
+            return ResultDict(vertices=verts.astype("float32"), faces=faces.astype("int32"))
+        except Exception as e:            # noqa: BLE001 -- called from C++ with no handler (LocalMapping_util.cc:194-196)
+            _warn_once(("extract_mesh", type(e).__name__), f"extract_mesh_from_code failed softly: {e!r}")
+            return ResultDict(vertices=np.zeros((0, 3), np.float32), faces=np.zeros((0, 3), np.int32))

@@ -43,6 +43,7 @@ extern "C" {
 #define DSPGN_E_CUDA (-2)     /* CUDA runtime error; see dspgn_last_error() */
 #define DSPGN_E_NOGPU (-3)    /* no usable sm_100 device */
 #define DSPGN_E_ALLOC (-4)
+#define DSPGN_E_PEER (-5)     /* multi-GPU exchange: a peer never published its results (timeout) */
 
 /* DspgnObjectOut.status (per-object soft failure = the reference's is_good=False exits) */
 #define DSPGN_ST_OK 0
@@ -50,6 +51,7 @@ extern "C" {
 #define DSPGN_ST_RENDER_FEW 2  /* loss.py:72-73 (fewer than 10 samples in the unit sphere) */
 #define DSPGN_ST_RENDER_NAN 3  /* optimizer.py:149-150 (no band rows -> NaN loss) */
 #define DSPGN_ST_SOLVE 4       /* normal matrix not positive definite / non-finite step */
+#define DSPGN_ST_BAD_INPUT 5   /* unusable detection (no surface points, too many rays, ...): never evaluated */
 
 /* decoder engines */
 #define DSPGN_ENGINE_AUTO 0
@@ -125,6 +127,7 @@ void dspgn_solver_destroy(DspgnSolver* s);
 /* stream = a cudaStream_t (NULL = legacy default stream). Work is enqueued on it. */
 int dspgn_solver_set_stream(DspgnSolver* s, void* cuda_stream);
 int dspgn_solver_engine(const DspgnSolver* s);   /* resolved DSPGN_ENGINE_* */
+int dspgn_solver_sync(DspgnSolver* s);           /* wait for everything enqueued on the solver's stream */
 
 /* Whole call, host buffers in, host buffers out (upload + all GN iterations + download + sync). */
 int dspgn_reconstruct_batch(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, DspgnObjectOut* out);
@@ -158,12 +161,47 @@ typedef struct {
 int dspgn_counters(DspgnSolver* s, DspgnCounters* out);
 int dspgn_enable_timing(DspgnSolver* s, int on);
 
+/* ---- Multi-GPU result exchange (the reference reconstructs objects one by one on one GPU,
+ * src/LocalMapping_util.cc:165-203 -- objects are independent, so a batch is sharded object-per-GPU).
+ * One process per GPU.  There is no collective kernel: rank 0 owns a "gather buffer" in its HBM, exports it
+ * with CUDA IPC, every other rank maps it over NVLink/NVSwitch, and the solve step that finishes an object
+ * stores the object's 352-byte result record STRAIGHT INTO rank 0's buffer (peer st.global issued from the
+ * same kernel that runs the tcgen05 tiles), at the object's slot = its index in the original batch.  A
+ * per-rank sequence flag (release, system scope) publishes a finished step; rank 0 waits for all flags with
+ * a one-warp kernel on its own stream.  Two slot sets alternate by step parity and rank 0 acknowledges
+ * consumed steps, so ranks may run at most one step ahead of rank 0.  `seq` = 1, 2, 3, ... (caller-owned,
+ * identical on all ranks).
+ *   rank 0:   gather_create -> (handle to the peers by any host channel) ;  ranks 1..: gather_open
+ *   per step, every rank:  upload_batch ; gather_bind(slots) ; run_batch_gather(mode, seq)
+ *   rank 0:   gather_results(seq, n, out)  (D2H + sync)   or   gather_device(seq) to keep them in HBM */
+#define DSPGN_IPC_HANDLE_BYTES 64
+typedef struct { unsigned char bytes[DSPGN_IPC_HANDLE_BYTES]; } DspgnIpcHandle;
+int dspgn_gather_create(DspgnSolver* s, int n_slots, int world, DspgnIpcHandle* handle_out);
+int dspgn_gather_open(DspgnSolver* s, const DspgnIpcHandle* handle, int n_slots, int world, int rank);
+/* slots[i] = slot of resident object i (n == resident objects); n == 0: this rank owns no object this step */
+int dspgn_gather_bind(DspgnSolver* s, const int32_t* slots, int n);
+int dspgn_run_batch_gather(DspgnSolver* s, int mode, int seq);
+int dspgn_gather_results(DspgnSolver* s, int seq, int n, DspgnObjectOut* out);
+const float* dspgn_gather_device(DspgnSolver* s, int seq);
+/* device time the root's wait kernel spent spinning in the last run_batch_gather (ns, after a sync); -1 if n/a */
+long long dspgn_gather_wait_ns(DspgnSolver* s);
+void dspgn_gather_close(DspgnSolver* s);
+
+/* Test hook: Lie-group exponentials exactly as the solve step applies them (loss_utils.py:129-233):
+ * x (n,7) -> out (n,12) row-major 3x4 [sR | J v]; sim3 = 0 ignores x[6] (exp_se3). */
+int dspgn_debug_exp(int device, int sim3, const float* x, int n, float* out);
+
 /* Test hook: evaluate one GN iteration at the uploaded initial state of object `obj` WITHOUT
  * updating it and return the assembled system: H (P*P row-major), b (P), dx (P), P = 7+code_len
  * (mode 0) or 6 (mode 1); J_rows/res_rows (may be NULL): the SDF-term Jacobian rows (n_pts,P) and
  * residuals (n_pts) as loss.compute_sdf_loss returns them. */
 int dspgn_debug_system(DspgnSolver* s, int obj, int mode, float* H, float* b, float* dx,
                        float* J_rows, float* res_rows, float* losses /* [sdf, render, V, m] */);
+/* The same after advancing the uploaded batch `iter` GN iterations from its initial state (iter = 0: identical
+ * to dspgn_debug_system): the system the (iter+1)-th iteration solves, for iteration-by-iteration parity
+ * against the reference's captured H/b/dx of every iteration (tests/golden/recon_*.npz H_iters[iter]). */
+int dspgn_debug_system_iter(DspgnSolver* s, int obj, int mode, int iter, float* H, float* b, float* dx,
+                            float* J_rows, float* res_rows, float* losses);
 
 /* Debug: clock64 timeline of CTA 0 of the tensor-core decoder kernel, [4 tiles][18 steps][8 slots]
  * (only when the solver was created with env DSPGN_CLK set). */

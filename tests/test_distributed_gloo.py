@@ -55,6 +55,58 @@ def test_shard_and_gather_world2(tmp_path, n_obj):
     assert all(x.t_cam_obj is None for x in res if not x.is_good)
 
 
+class _FakeSolver:
+    """Deterministic stand-in for a per-rank BatchSolver (no GPU here): same upload / run / results_raw surface."""
+
+    def __init__(self):
+        self.objs = []
+
+    def upload(self, objs):
+        self.objs = list(objs)
+
+    def run(self, mode=0):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def set_stream(self, s):
+        pass
+
+    def results_raw(self):
+        return np.stack([_fake_record(int(o["obj_id"]), int(o.get("class_id", 0))) for o in self.objs]).reshape(-1)
+
+
+class _FakeOptimizer:
+    def __init__(self):
+        self.solver, self.device, self.code_len = _FakeSolver(), 0, 64
+
+
+def _worker_sharded(rank, world, port, n_obj, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dsp_slam_b200.distributed import ShardedOptimizer
+    objs = [dict(obj_id=i, class_id=(i * 7) % 3) for i in range(n_obj)]       # the SAME full list on every rank
+    sh = ShardedOptimizer(_FakeOptimizer(), exchange="nccl")                   # collective mechanism (gloo here)
+    res = sh.reconstruct_batch(objs)
+    np.save(os.path.join(out_dir, f"s{rank}.npy"),
+            np.array([[r.is_good, r.loss, -1 if r.code is None else r.code[0]] for r in res], dtype=np.float64))
+    assert len(sh._idx) in (n_obj // world, n_obj // world + 1)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_obj", [1, 9, 32])
+def test_sharded_optimizer_world2_gloo(tmp_path, n_obj):
+    """ShardedOptimizer.reconstruct_batch end to end over a world_size-2 gloo group: class-sorted shard of ONE
+    list, per-rank solve (stand-in solver), all-gather, results back in the original order on every rank."""
+    port = _free_port()
+    mp.spawn(_worker_sharded, args=(2, port, n_obj, str(tmp_path)), nprocs=2, join=True)
+    want = np.array([[i % 5 != 3, 0.5 * i, i if i % 5 != 3 else -1] for i in range(n_obj)], dtype=np.float64)
+    for r in range(2):
+        np.testing.assert_array_equal(np.load(tmp_path / f"s{r}.npy"), want)
+
+
 def test_shard_plan_properties():
     from dsp_slam_b200.distributed import shard_plan
     rng = np.random.default_rng(0)
