@@ -93,9 +93,12 @@ struct DspgnSolver {
   DevBuf d_sdf, d_bx, d_bs, d_br;
   DevBuf d_dbg;
   DevBuf d_q_items, d_q_flag, d_q_ctr, d_tiles_left, d_obj_iter;   // persistent-kernel work queue
-  int* d_tbase_static = nullptr;   // [n_obj] first 128-row tile of each object (inside the staging block)
-  int total_tiles128 = 0;
-  int max_tiles128 = 0;          // tiles of the largest object (work-queue items pack the tile index into 16 bits)
+  int* d_tbase_static = nullptr;   // [n_obj] first 128-row SDF tile of each object (inside the staging block)
+  int* d_tbase_r_static = nullptr; // [n_obj] first band-tile partial slot of each object (capacity: its ray-sample tiles + 1)
+  int* d_q0_render = nullptr;      // [n_obj] first iteration-0 queue slot of each object in a run with the render term
+  int total_tiles128 = 0;          // SDF tiles of the batch
+  long long total_ray_tiles128 = 0;// ray-sample tiles of the batch
+  int max_tiles128 = 0;            // largest tile count of one term of one object (queue items hold 19 bits)
   bool mega_enabled = true;
   DevBuf d_clk;
   bool clk_on = false;
@@ -112,6 +115,7 @@ struct DspgnSolver {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_upload = nullptr;   // the pinned staging block may be rewritten only after its last H2D copy finished
   bool upload_pending = false;
+  bool band_rows_pending = false;    // the persistent kernel's band-row total has not been added to ctr yet
   int n_bad = 0;                     // resident objects rejected at upload (status BAD_INPUT, never evaluated)
   // multi-GPU result exchange (rank 0 owns the buffer, the others map it through CUDA IPC)
   struct Gather {
@@ -378,7 +382,7 @@ int upload_batch_impl(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, bool d
   const size_t o_meta = 0, o_T = al(o_meta + sizeof(ObjMeta) * n_obj), o_code = al(o_T + 64 * n_obj),
                o_pts = al(o_code + 4 * kMaxCode * (size_t)n_obj), o_rays = al(o_pts + 12 * (size_t)tp),
                o_depth = al(o_rays + 12 * (size_t)tr), o_tb = al(o_depth + 4 * (size_t)tf),
-               total = al(o_tb + 4 * (size_t)n_obj);
+               total = al(o_tb + 3 * 4 * (size_t)n_obj);
   if (s->upload_pending) { CU(cudaEventSynchronize(s->ev_upload)); s->upload_pending = false; }
   if (s->d_stage.cap < total) CU(cudaStreamSynchronize(s->stream));      // kernels of an earlier batch may still read the old block
   if (s->h_stage.reserve(total) || s->d_stage.reserve(total)) return fail(DSPGN_E_ALLOC, "staging allocation failed");
@@ -391,13 +395,19 @@ int upload_batch_impl(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, bool d
   float* hD = reinterpret_cast<float*>(hb + o_depth);
   int* hTB = reinterpret_cast<int*>(hb + o_tb);
   {
-    int acc = 0;
-    int mx = 0;
+    int acc = 0, mx = 0;
+    long long accr = 0, accq = 0;
+    int* hTBr = hTB + n_obj;
+    int* hQ0 = hTB + 2 * n_obj;
     for (int o = 0; o < n_obj; ++o) {
       const int nt = (s->h_meta[o].n_pts + kTcRows - 1) / kTcRows;
-      hTB[o] = acc; acc += nt; if (nt > mx) mx = nt;
+      const int ntf = (int)(((long long)s->h_meta[o].n_rays * D + kTcRows - 1) / kTcRows);
+      hTB[o] = acc; hTBr[o] = (int)(accr + o); hQ0[o] = (int)accq;
+      acc += nt; accr += ntf; accq += nt + ntf;
+      if (nt > mx) mx = nt;
+      if (ntf > mx) mx = ntf;
     }
-    s->total_tiles128 = acc; s->max_tiles128 = mx;
+    s->total_tiles128 = acc; s->total_ray_tiles128 = accr; s->max_tiles128 = mx;
   }
   for (int o = 0; o < n_obj; ++o) {
     const DspgnObjectIn& I = in[o];
@@ -425,6 +435,8 @@ int upload_batch_impl(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, bool d
   s->d_rays = reinterpret_cast<float*>(db + o_rays);
   s->d_depth = reinterpret_cast<float*>(db + o_depth);
   s->d_tbase_static = reinterpret_cast<int*>(db + o_tb);
+  s->d_tbase_r_static = s->d_tbase_static + n_obj;
+  s->d_q0_render = s->d_tbase_static + 2 * n_obj;
   s->n_obj = n_obj; s->tot_pts = (int)tp; s->tot_rays = (int)tr; s->tot_fg = (int)tf; s->tot_smp = ts; s->max_rays = max_rays;
   s->gather.bound_n = -1;
   int bad = 0;
@@ -433,7 +445,7 @@ int upload_batch_impl(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, bool d
   if (!decode_only) {
     // per-tile partial sums: one slot per possible tile of each term at the engine's tile height
     const size_t rows_per_tile = (s->engine == DSPGN_ENGINE_TC) ? kTcRows : kTP;
-    const size_t tiles_s = (size_t)tp / rows_per_tile + n_obj + 1, tiles_r = (size_t)ts / rows_per_tile + n_obj + 1;
+    const size_t tiles_s = (size_t)tp / rows_per_tile + n_obj + 1, tiles_r = (size_t)ts / rows_per_tile + 2 * (size_t)n_obj + 1;
     bad |= s->d_part_s.reserve(4 * (size_t)kAccStride * tiles_s);
     if (render) bad |= s->d_part_r.reserve(4 * (size_t)kAccStride * tiles_r);
     bad |= s->d_active.reserve((size_t)tp + 1);
@@ -502,7 +514,7 @@ TermArgs base_term(DspgnSolver* s, int mode) {
   return a;
 }
 
-int launch_init(DspgnSolver* s, int pose_only, bool mega = false) {
+int launch_init(DspgnSolver* s, int pose_only, bool mega = false, bool render = false) {
   InitArgs ia{};
   ia.meta = s->d_meta; ia.state = s->d_state.as<ObjState>(); ia.T_init = s->d_Tinit; ia.code_init = s->d_code;
   ia.V_count = s->d_V.as<int>(); ia.band_m = s->d_m.as<int>();
@@ -511,15 +523,29 @@ int launch_init(DspgnSolver* s, int pose_only, bool mega = false) {
   ia.gather = s->gdev; ia.results = s->d_results.as<float>(); ia.n_bad = s->n_bad;
   ia.mega = mega ? 1 : 0;
   if (mega) {
-    ia.tile_base = s->d_tbase_static; ia.tile_rows = kTcRows;
+    ia.render = render ? 1 : 0;
+    ia.q0_off = render ? s->d_q0_render : s->d_tbase_static; ia.tile_rows = kTcRows;
     ia.q_items = s->d_q_items.as<int>(); ia.q_flag = s->d_q_flag.as<int>();
     ia.q_head = s->d_q_ctr.as<int>(); ia.q_tail = s->d_q_ctr.as<int>() + 32; ia.done_objects = s->d_q_ctr.as<int>() + 64;
-    ia.tiles_left = s->d_tiles_left.as<int>(); ia.obj_iter = s->d_obj_iter.as<int>(); ia.total_tiles0 = s->total_tiles128;
+    ia.band_rows_total = s->d_q_ctr.as<int>() + 80;
+    ia.pending = s->d_tiles_left.as<int>(); ia.ray_left = s->d_tiles_left.as<int>() + s->n_obj;
+    ia.obj_iter = s->d_obj_iter.as<int>();
+    ia.total_tiles0 = s->total_tiles128 + (render ? (int)s->total_ray_tiles128 : 0);
   }
   k_init<<<s->n_obj, 128, 0, s->stream>>>(ia);
   s->ctr.kernel_launches++;
   CU(cudaGetLastError());
   return 0;
+}
+
+ScanArgs base_scan(DspgnSolver* s) {
+  const DspgnConfig& c = s->cfg;
+  ScanArgs sa{};
+  sa.meta = s->d_meta; sa.state = s->d_state.as<ObjState>(); sa.rays = s->d_rays; sa.depth_fg = s->d_depth;
+  sa.sdf = s->d_sdf.as<float>(); sa.band_x = s->d_bx.as<float>(); sa.band_s = s->d_bs.as<float>();
+  sa.band_r = s->d_br.as<float>(); sa.band_m = s->d_m.as<int>(); sa.th = c.cut_off; sa.D = c.num_depth_samples;
+  sa.n_obj = s->n_obj;
+  return sa;
 }
 
 // one GN iteration's residual-term kernels (everything before the solve)
@@ -556,11 +582,7 @@ int launch_terms(DspgnSolver* s, int pose_only, float* dbg_J, float* dbg_res, in
   }
   if (render) {
     if (fork) CU(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
-    ScanArgs sa{};
-    sa.meta = s->d_meta; sa.state = s->d_state.as<ObjState>(); sa.rays = s->d_rays; sa.depth_fg = s->d_depth;
-    sa.sdf = s->d_sdf.as<float>(); sa.band_x = s->d_bx.as<float>(); sa.band_s = s->d_bs.as<float>();
-    sa.band_r = s->d_br.as<float>(); sa.band_m = s->d_m.as<int>(); sa.th = c.cut_off; sa.D = c.num_depth_samples;
-    sa.n_obj = s->n_obj;
+    ScanArgs sa = base_scan(s);
     k_ray_scan<<<s->n_obj, kScanThreads, 0, s->stream>>>(sa);
     s->ctr.kernel_launches++;
     CU(cudaGetLastError());
@@ -598,41 +620,51 @@ int run_batch_impl(DspgnSolver* s, int mode) {
   const int pose_only = mode;
   const int iters = pose_only ? s->cfg.pose_only_iterations : s->cfg.num_iterations;
   s->ctr = DspgnCounters{};
+  s->band_rows_pending = false;
   s->ev_used = 0;
   s->evs_used = 0;
   CU(cudaEventRecord(s->ev_run0, s->stream));
-  const bool mega = s->mega_enabled && s->engine == DSPGN_ENGINE_TC && (pose_only || s->cfg.sdf_only) &&
-                    s->total_tiles128 > 0 && s->max_tiles128 <= 0xffff && (long long)s->total_tiles128 * iters < (1LL << 28);
+  const bool render = !pose_only && !s->cfg.sdf_only;
+  // queue capacity: per iteration every SDF tile, every ray-sample tile and at most as many band tiles again
+  const long long items_per_iter = (long long)s->total_tiles128 + (render ? 2 * s->total_ray_tiles128 : 0);
+  const bool mega = s->mega_enabled && s->engine == DSPGN_ENGINE_TC && s->total_tiles128 > 0 &&
+                    s->max_tiles128 <= kItemTileMask && s->n_obj <= kItemObjMask + 1 && items_per_iter * iters < (1LL << 27);
   if (mega) {
     // ---- persistent object-pipelined kernel: every GN iteration of every object in ONE launch --------------
-    const int cap = s->total_tiles128 * iters;
+    const int cap = (int)(items_per_iter * iters);
     int bad = 0;
     bad |= s->d_q_items.reserve(4 * (size_t)cap);
     bad |= s->d_q_flag.reserve(4 * (size_t)cap);
-    bad |= s->d_q_ctr.reserve(4 * 96);
-    bad |= s->d_tiles_left.reserve(4 * (size_t)s->n_obj);
+    bad |= s->d_q_ctr.reserve(4 * 128);
+    bad |= s->d_tiles_left.reserve(4 * 2 * (size_t)s->n_obj);
     bad |= s->d_obj_iter.reserve(4 * (size_t)s->n_obj);
     if (bad) return fail(DSPGN_E_ALLOC, "queue allocation failed");
     CU(cudaMemsetAsync(s->d_q_flag.p, 0, 4 * (size_t)cap, s->stream));
-    if (int rc = launch_init(s, pose_only, true)) return rc;
+    if (int rc = launch_init(s, pose_only, true, render)) return rc;
     TermArgs a = base_term(s, MODE_SDF);
     a.huber_b = pose_only ? INFINITY : s->cfg.b2;
+    a.huber_b1 = s->cfg.b1;
     a.pose_only = pose_only;
     a.tile_base = s->d_tbase_static;
+    a.part_r = s->d_part_r.as<float>(); a.tile_base_r = s->d_tbase_r_static;
     a.dbg_clk = nullptr;
     if (pose_only && iters > 5) { a.pt_active_out = s->d_active.as<uint8_t>(); a.cut_iter = 4; }
     MegaArgs q{};
-    q.n_iters = iters; q.q_cap = cap;
+    q.n_iters = iters; q.q_cap = cap; q.render = render ? 1 : 0;
     q.q_items = s->d_q_items.as<int>(); q.q_flag = s->d_q_flag.as<int>();
     q.q_head = s->d_q_ctr.as<int>(); q.q_tail = s->d_q_ctr.as<int>() + 32; q.done_objects = s->d_q_ctr.as<int>() + 64;
-    q.tiles_left = s->d_tiles_left.as<int>(); q.obj_iter = s->d_obj_iter.as<int>();
+    q.band_rows_total = s->d_q_ctr.as<int>() + 80;
+    q.pending = s->d_tiles_left.as<int>(); q.ray_left = s->d_tiles_left.as<int>() + s->n_obj; q.obj_iter = s->d_obj_iter.as<int>();
     SolveArgs v = base_solve(s, pose_only);
-    v.base_s = s->d_tbase_static; v.tile_rows = kTcRows; v.last_iter = 0; v.iter_index = 0; v.dbg_clk = nullptr;
+    v.base_s = s->d_tbase_static; v.base_r = s->d_tbase_r_static; v.tile_rows = kTcRows; v.last_iter = 0; v.iter_index = 0; v.dbg_clk = nullptr;
+    ScanArgs sa = base_scan(s);
     if (s->timing) cudaEventRecord(next_event(s), s->stream);
-    k_gn_persistent<<<s->num_sms, kTcThreads, kTcSmemBytes, s->stream>>>(a, q, v);
+    k_gn_persistent<<<s->num_sms, kTcThreads, kTcSmemBytes, s->stream>>>(a, q, v, sa);
     if (s->timing) cudaEventRecord(next_event(s), s->stream);
     s->ctr.kernel_launches += 1;
     s->ctr.rows_fwd_bwd += (long long)s->tot_pts * iters;
+    if (render) s->ctr.rows_fwd_only += s->tot_smp * iters;
+    s->band_rows_pending = render;
     CU(cudaGetLastError());
     CU(cudaEventRecord(s->ev_run1, s->stream));
     return 0;
@@ -833,6 +865,12 @@ int dspgn_results(DspgnSolver* s, DspgnObjectOut* out) {
   CU(cudaMemcpyAsync(s->h_results.p, s->d_results.p, bytes, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   memcpy(out, s->h_results.p, bytes);
+  if (s->band_rows_pending) {          // band rows the persistent kernel processed (data dependent): roofline accounting
+    int m_total = 0;
+    if (cudaMemcpy(&m_total, s->d_q_ctr.as<int>() + 80, 4, cudaMemcpyDeviceToHost) == cudaSuccess) s->ctr.rows_fwd_bwd += m_total;
+    else cudaGetLastError();
+    s->band_rows_pending = false;
+  }
   if (s->timing) {
     float dec = 0.f;
     for (size_t i = 0; i + 1 < s->ev_used; i += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]); dec += ms; }

@@ -51,6 +51,8 @@ struct TermArgs {
   float* part;               // per-tile partial sums of this term: [tile][kAccStride] (H upper | b | loss, rows)
   int* tile_base;            // [n_obj] first tile of each object in this launch (written by CTA 0)
   float huber_b;
+  // persistent kernel with the render term: the band rows' partials / tile bases / Huber threshold (SDF ones above)
+  float* part_r; const int* tile_base_r; float huber_b1;
   int D;
   int pose_only;             // 1: 6-D se3 Jacobian (no scale column)
   // debug dump of Jacobian rows (external order [pose | code]) for one object
@@ -58,15 +60,24 @@ struct TermArgs {
   long long* dbg_clk;         // optional phase timeline of CTA 0 (tensor-core engine)
 };
 
-// Device work queue of the persistent object-pipelined kernel (dspgn_tc.cuh): items = (object << 16 | tile).
+// Device work queue of the persistent object-pipelined kernel (dspgn_tc.cuh).
+// item = kind << 29 | object << 19 | tile   (kind: the tile's MODE_*; object < 1024; tile < 2^19; always >= 0)
+constexpr int kItemKindShift = 29, kItemObjShift = 19, kItemTileMask = (1 << 19) - 1, kItemObjMask = 1023;
+__host__ __device__ __forceinline__ int make_item(int kind, int o, int tile) {
+  return (kind << kItemKindShift) | (o << kItemObjShift) | tile;
+}
 struct MegaArgs {
   int n_iters;               // GN iterations per object
-  int q_cap;                 // total items that can ever be pushed (sum of tiles x iterations)
+  int q_cap;                 // total items that can ever be pushed
+  int render;                // 1: joint run with the render term (ray-sample tiles -> per-ray scan -> band tiles)
   int* q_items; int* q_flag; // item payload / published flag per slot (no wrap-around)
   int* q_head; int* q_tail;  // consumer ticket counter / producer reservation counter
-  int* tiles_left;           // [n_obj] tiles of the object's current iteration still running
+  int* pending;              // [n_obj] SDF + band tiles of the object's current iteration still running (+1 while the
+                             //         render term has not been expanded into band tiles yet)
+  int* ray_left;             // [n_obj] ray-sample tiles of the current iteration still running
   int* obj_iter;             // [n_obj] current iteration of each object
   int* done_objects;         // objects finished (last iteration or frozen)
+  int* band_rows_total;      // sum of band rows over all objects and iterations (roofline accounting)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -4,6 +4,7 @@
 // Restates optimizer.py:45-86, 97-203; loss.py:84-141, 155-178; loss_utils.py:188-233.
 #pragma once
 #include "dspgn_common.cuh"
+#include "dspgn_simt.cuh"
 
 namespace dspgn {
 
@@ -117,9 +118,9 @@ struct InitArgs {
   int* band_m;
   uint8_t* pt_active;      // [total_pts] reset to 1 (pose-only mode)
   int n_obj, code_len, D, pose_only;
-  // persistent-kernel mode: also seed the work queue with every object's iteration-0 tiles
-  int mega; const int* tile_base; int tile_rows; int* q_items; int* q_flag; int* q_head; int* q_tail;
-  int* tiles_left; int* obj_iter; int* done_objects; int total_tiles0;
+  // persistent-kernel mode: also seed the work queue with every object's iteration-0 tiles (ray-sample tiles first)
+  int mega; int render; const int* q0_off; int tile_rows; int* q_items; int* q_flag; int* q_head; int* q_tail;
+  int* pending; int* ray_left; int* obj_iter; int* done_objects; int* band_rows_total; int total_tiles0;
   GatherDev gather;
   float* results;          // records of objects rejected at upload are written here
   int n_bad;
@@ -151,10 +152,13 @@ __global__ void k_init(InitArgs a) {
     if (tid == 0) write_record(a.results, a.gather, o, st, a.pose_only, M.scale);
   }
   if (a.mega) {
-    const int nt = (M.n_pts + a.tile_rows - 1) / a.tile_rows, base = a.tile_base[o];
-    for (int j = tid; j < nt; j += blockDim.x) { a.q_items[base + j] = (o << 16) | j; a.q_flag[base + j] = 1; }
-    if (tid == 0) { a.tiles_left[o] = nt; a.obj_iter[o] = 0; }
-    if (o == 0 && tid == 0) { *a.q_head = 0; *a.q_tail = a.total_tiles0; *a.done_objects = a.n_bad; }
+    const int ntS = (M.n_pts + a.tile_rows - 1) / a.tile_rows;
+    const int ntF = (a.render && !M.bad) ? (M.n_rays * a.D + a.tile_rows - 1) / a.tile_rows : 0;
+    const int base = a.q0_off[o];
+    for (int j = tid; j < ntF; j += blockDim.x) { a.q_items[base + j] = make_item(MODE_RAYFWD, o, j); a.q_flag[base + j] = 1; }
+    for (int j = tid; j < ntS; j += blockDim.x) { a.q_items[base + ntF + j] = make_item(MODE_SDF, o, j); a.q_flag[base + ntF + j] = 1; }
+    if (tid == 0) { a.pending[o] = ntS + (ntF > 0 ? 1 : 0); a.ray_left[o] = ntF; a.obj_iter[o] = 0; }
+    if (o == 0 && tid == 0) { *a.q_head = 0; *a.q_tail = a.total_tiles0; *a.done_objects = a.n_bad; *a.band_rows_total = 0; }
   }
 }
 
@@ -236,7 +240,7 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
   const bool dbg = (a.dbg_H != nullptr);
   const bool use_render = !a.pose_only && !prm.sdf_only;
   // tile partials of this object, summed in tile order (deterministic), fp64
-  const int V = a.V_count[o], m = use_render ? a.band_m[o] : 0;
+  const int V = ldv(a.V_count + o), m = use_render ? ldv(a.band_m + o) : 0;
   const int ntS = (a.meta[o].n_pts + a.tile_rows - 1) / a.tile_rows;
   const int ntR = use_render ? (m + a.tile_rows - 1) / a.tile_rows : 0;
   const float* pS = a.part_s + (size_t)a.base_s[o] * kAccStride;
@@ -501,7 +505,16 @@ struct ScanArgs {
 constexpr int kScanThreads = 1024;
 constexpr int kScanMaxRays = 8192;
 
-__device__ __forceinline__ void ray_scan(const ScanArgs& a, const ObjMeta& M, const ObjState& st, int ray, int lane,
+// pose / depth range of the object being scanned, read once per thread (cache-bypassing: in the persistent kernel
+// another CTA's solve wrote it)
+struct ScanState { float T[12]; float dmin, dmax, dstep, dfar; };
+__device__ __forceinline__ void load_scan_state(const ObjState& st, ScanState& c) {
+#pragma unroll
+  for (int i = 0; i < 12; ++i) c.T[i] = ldv(&st.T_oc[i]);
+  c.dmin = ldv(&st.dmin); c.dmax = ldv(&st.dmax); c.dstep = ldv(&st.dstep); c.dfar = ldv(&st.dfar);
+}
+
+__device__ __forceinline__ void ray_scan(const ScanArgs& a, const ObjMeta& M, const ScanState& st, int ray, int lane,
                                          bool keep[2], float de_ds[2], float& res) {
   const int D = a.D;
   const float th = a.th;
@@ -510,7 +523,7 @@ __device__ __forceinline__ void ray_scan(const ScanArgs& a, const ObjMeta& M, co
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int j = lane + 32 * h;
-    s[h] = (j < D) ? srow[j] : INFINITY;
+    s[h] = (j < D) ? __ldcg(srow + j) : INFINITY;    // written by other CTAs (L2 is the point of coherence)
     o[h] = (j < D) ? occupancy(s[h], th) : 0.f;      // +inf -> clamp -> 0 (outside sphere: loss.py:84)
     q[h] = 1.f - o[h];
   }
@@ -559,13 +572,20 @@ __device__ __forceinline__ void ray_scan(const ScanArgs& a, const ObjMeta& M, co
   res = fminf(fmaxf(dobs - du, -0.3f), 0.3f);           // loss.py:136-141
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_ray_scan(ScanArgs a) {
-  __shared__ int s_cnt[kScanMaxRays];
-  __shared__ int s_wsum[32];
-  const int o = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = kScanThreads / 32;
+// The per-object scan: called by all `nthreads` threads of k_ray_scan's CTA (MEGA = false) or by the 256 epilogue
+// threads of the persistent kernel's CTA that finished the object's last ray-sample tile (MEGA = true).
+// s_cnt: kScanMaxRays ints, s_wsum: 32 ints of shared memory.
+template <bool MEGA>
+__device__ __forceinline__ void scan_sync() {
+  if (MEGA) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else __syncthreads();
+}
+template <bool MEGA>
+__device__ inline void scan_object(const ScanArgs& a, const int o, const int tid, const int nthreads, int* s_cnt, int* s_wsum) {
+  const int lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
   const ObjMeta M = a.meta[o];
-  const ObjState& st = a.state[o];
-  if (st.status != 0) return;
+  ScanState st;
+  load_scan_state(a.state[o], st);
   const int N = M.n_rays;
   bool keep[2]; float de_ds[2]; float res;
   for (int ray = warp; ray < N; ray += nw) {
@@ -573,22 +593,22 @@ __global__ void __launch_bounds__(kScanThreads) k_ray_scan(ScanArgs a) {
     const int c = __popc(__ballot_sync(0xffffffffu, keep[0])) + __popc(__ballot_sync(0xffffffffu, keep[1]));
     if (lane == 0) s_cnt[ray] = c;
   }
-  __syncthreads();
+  scan_sync<MEGA>();
   // block exclusive scan of s_cnt[0..N)
   int carry = 0;
-  for (int base = 0; base < N; base += kScanThreads) {
+  for (int base = 0; base < N; base += nthreads) {
     const int i = base + tid;
     const int v = (i < N) ? s_cnt[i] : 0;
     int x = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
     if (lane == 31) s_wsum[warp] = x;
-    __syncthreads();
+    scan_sync<MEGA>();
     int woff = 0, tot = 0;
     for (int w = 0; w < nw; ++w) { if (w < warp) woff += s_wsum[w]; tot += s_wsum[w]; }
     if (i < N) s_cnt[i] = carry + woff + x - v;
     carry += tot;
-    __syncthreads();
+    scan_sync<MEGA>();
   }
   if (tid == 0) a.band_m[o] = carry;
   for (int ray = warp; ray < N; ray += nw) {
@@ -603,13 +623,21 @@ __global__ void __launch_bounds__(kScanThreads) k_ray_scan(ScanArgs a) {
       const int pos = base + (h == 0 ? __popc(b0 & ((1u << lane) - 1u)) : __popc(b0) + __popc(b1 & ((1u << lane) - 1u)));
       const float d = lin_depth(st.dmin, st.dmax, st.dstep, j, a.D);
       float x, y, z;
-      xform_point(st.T_oc, __fmul_rn(q[0], d), __fmul_rn(q[1], d), __fmul_rn(q[2], d), x, y, z);
+      xform_point(st.T, __fmul_rn(q[0], d), __fmul_rn(q[1], d), __fmul_rn(q[2], d), x, y, z);
       const size_t row = (size_t)M.smp_off + pos;
       a.band_x[3 * row] = x; a.band_x[3 * row + 1] = y; a.band_x[3 * row + 2] = z;
       a.band_s[row] = de_ds[h];
       a.band_r[row] = res;
     }
   }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_ray_scan(ScanArgs a) {
+  __shared__ int s_cnt[kScanMaxRays];
+  __shared__ int s_wsum[32];
+  const int o = blockIdx.x;
+  if (a.state[o].status != 0) return;
+  scan_object<false>(a, o, threadIdx.x, kScanThreads, s_cnt, s_wsum);
 }
 
 }  // namespace dspgn

@@ -232,7 +232,7 @@ __device__ __forceinline__ void unit_done(uint64_t* bar) {
   mbar_arrive(bar);
 }
 
-struct TileRef { int o, row0, slot; };
+struct TileRef { int o, row0, slot, mode, tile; };
 
 // pop one work item for this CTA (persistent mode); -1 = no more work anywhere
 __device__ inline int mega_pop(const MegaArgs& q, int n_obj) {
@@ -253,24 +253,44 @@ __device__ __forceinline__ bool tile_at(const TermArgs& a, TcSmemTail& S, int se
     const int tile = blockIdx.x + seq * gridDim.x;
     if (tile >= total_tiles) return false;
     t.o = find_object(S.prefix, a.n_obj, tile);
-    t.row0 = (tile - S.prefix[t.o]) * kTcRows;
+    t.tile = tile - S.prefix[t.o];
+    t.row0 = t.tile * kTcRows;
     t.slot = tile;
+    t.mode = a.mode;
     return true;
   } else {
     volatile int* pub = &S.fifo_pub;
     for (unsigned spins = 0; *pub <= seq; ++spins) { __nanosleep(64); if (spins > (1u << 26)) __trap(); }
     const int item = reinterpret_cast<volatile int*>(S.fifo)[seq & 3];
     if (item < 0) return false;
-    t.o = item >> 16;
-    const int j = item & 0xffff;
+    t.o = (item >> kItemObjShift) & kItemObjMask;
+    t.mode = item >> kItemKindShift;
+    const int j = item & kItemTileMask;
+    t.tile = j;
     t.row0 = j * kTcRows;
-    t.slot = a.tile_base[t.o] + j;
+    t.slot = (t.mode == MODE_BAND) ? a.tile_base_r[t.o] + j : (t.mode == MODE_SDF ? a.tile_base[t.o] + j : 0);
     return true;
   }
 }
 
+// rows of the term a tile belongs to (persistent kernel: the tile's own kind, counters written by other CTAs)
+__device__ __forceinline__ int mega_rows(const TermArgs& a, const ObjMeta& M, int o, int mode) {
+  if (mode == MODE_SDF) return M.n_pts;
+  if (mode == MODE_BAND) return ldv(a.band_m + o);
+  return M.n_rays * a.D;
+}
+
+// publish `n` queue items (kind, object, tile 0..n-1): reserve slots, payload, fence, flags.  One thread.
+__device__ inline void mega_push(const MegaArgs& q, int kind, int o, int n) {
+  if (n <= 0) return;
+  const int base = atomicAdd(q.q_tail, n);
+  for (int j = 0; j < n; ++j) *reinterpret_cast<volatile int*>(q.q_items + base + j) = make_item(kind, o, j);
+  __threadfence();
+  for (int j = 0; j < n; ++j) *reinterpret_cast<volatile int*>(q.q_flag + base + j) = 1;
+}
+
 template <bool MEGA>
-__device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, const SolveArgs& sv) {
+__device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, const SolveArgs& sv, const ScanArgs& sc_args) {
   extern __shared__ unsigned char tc_smem_raw[];
   unsigned char* ring = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   TcSmemTail& S = *reinterpret_cast<TcSmemTail*>(ring + (size_t)kTcStages * kTcStageBytes);
@@ -297,7 +317,6 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
-  const bool fwd_only = (a.mode == MODE_RAYFWD || a.mode == MODE_PTSFWD);
 
   if (warp == 9) {
     // ===================== weight producer ======================================================
@@ -319,6 +338,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         const int cls = a.meta[o].class_id;
         const TcPlan& plan = S.plans[cls];
         const unsigned char* blob = a.decs[cls].tc_blob;
+        const bool fwd_only = (tr.mode == MODE_RAYFWD || tr.mode == MODE_PTSFWD);
         const int ns = fwd_only ? plan.n_fwd : plan.n_steps;
         for (int s = 0; s < ns; ++s) {
           const TcStep st = plan.step[s];
@@ -347,6 +367,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
       if (!tile_at<MEGA>(a, S, seq, total_tiles, tr)) break;
       const int o = tr.o;
       const TcPlan& plan = S.plans[a.meta[o].class_id];
+      const bool fwd_only = (tr.mode == MODE_RAYFWD || tr.mode == MODE_PTSFWD);
       const int ns = fwd_only ? plan.n_fwd : plan.n_steps;
       for (int s = 0; s < ns; ++s) {
         const TcStep st = plan.step[s];
@@ -413,15 +434,18 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
       TileRef tr;
       if (!tile_at<MEGA>(a, S, seq, total_tiles, tr)) break;
       if (MEGA && tid == 0) *reinterpret_cast<volatile int*>(&S.epi_seq) = seq + 1;
-      const int o = tr.o, row0 = tr.row0, tile = tr.slot;
+      const int o = tr.o, row0 = tr.row0, tile = tr.slot, mode = tr.mode;
       const ObjMeta M = a.meta[o];
       const ObjState& ost = a.state[o];
       const DecoderDev& dec = a.decs[M.class_id];
       const TcPlan& plan = S.plans[M.class_id];
       const int L = dec.L, in0 = dec.in0, n_lin = dec.n_lin;
       const bool has_skip = dec.latent_in >= 0;
-      const int nrows = min(kTcRows, (MEGA ? M.n_pts : term_rows(a, o)) - row0);
+      const bool fwd_only = (mode == MODE_RAYFWD || mode == MODE_PTSFWD);
+      const int nrows = min(kTcRows, (MEGA ? mega_rows(a, M, o, mode) : term_rows(a, o)) - row0);
       const int ns = fwd_only ? plan.n_fwd : plan.n_steps;
+      const float huber_b = (MEGA && mode == MODE_BAND) ? a.huber_b1 : a.huber_b;
+      float* const part = (MEGA && mode == MODE_BAND) ? a.part_r : a.part;
       // the pose / code of this object may have been rewritten by another CTA's solve: bypass L1
       float Toc[12];
 #pragma unroll
@@ -444,18 +468,19 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
       float x0 = 0.f, x1 = 0.f, x2 = 0.f, sc = 0.f, res_in = 0.f;
       if (r < nrows) {
         const int rr_ = row0 + r;
-        if (a.mode == MODE_SDF || a.mode == MODE_PTSFWD) {
+        if (mode == MODE_SDF || mode == MODE_PTSFWD) {
           const float* q = a.pts + 3 * (size_t)(M.pts_off + rr_);
           xform_point(Toc, q[0], q[1], q[2], x0, x1, x2);
           sc = (mask_in == nullptr || ldv(mask_in + M.pts_off + rr_)) ? 1.f : 0.f;
-        } else if (a.mode == MODE_BAND) {
+        } else if (mode == MODE_BAND) {
+          // band rows were written by the CTA that ran this object's scan: L2 is the point of coherence
           const size_t sidx = (size_t)M.smp_off + rr_;
-          x0 = a.band_x[3 * sidx]; x1 = a.band_x[3 * sidx + 1]; x2 = a.band_x[3 * sidx + 2];
-          sc = a.band_s[sidx]; res_in = a.band_r[sidx];
+          x0 = __ldcg(a.band_x + 3 * sidx); x1 = __ldcg(a.band_x + 3 * sidx + 1); x2 = __ldcg(a.band_x + 3 * sidx + 2);
+          sc = __ldcg(a.band_s + sidx); res_in = __ldcg(a.band_r + sidx);
         } else {
           const int ray = rr_ / a.D, j = rr_ - ray * a.D;
           const float* q = a.rays + 3 * (size_t)(M.ray_off + ray);
-          const float d = lin_depth(ost.dmin, ost.dmax, ost.dstep, j, a.D);
+          const float d = lin_depth(ldv(&ost.dmin), ldv(&ost.dmax), ldv(&ost.dstep), j, a.D);
           xform_point(Toc, __fmul_rn(q[0], d), __fmul_rn(q[1], d), __fmul_rn(q[2], d), x0, x1, x2);
           sc = (sqrtf(x0 * x0 + x1 * x1 + x2 * x2) < 1.0f) ? 1.f : 0.f;
         }
@@ -507,10 +532,10 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
           yv = tanhf(d0 + S.bias[st.layer * kHid]);                  // deep_sdf_decoder.py:107-108
           if (fwd_only) {
             if (grp == 0 && r < nrows) {
-              const size_t base = (a.mode == MODE_RAYFWD) ? (size_t)M.smp_off : (size_t)M.pts_off;
+              const size_t base = (mode == MODE_RAYFWD) ? (size_t)M.smp_off : (size_t)M.pts_off;
               a.sdf_out[base + row0 + r] = (sc != 0.f) ? yv : INFINITY;
             }
-            if (a.mode == MODE_RAYFWD) {
+            if (mode == MODE_RAYFWD) {
               const unsigned b = __ballot_sync(0xffffffffu, grp == 0 && r < nrows && sc != 0.f);
               if (lane == 0 && b) atomicAdd(a.V_count + o, __popc(b));
             }
@@ -618,8 +643,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         if (tid == 0) DSPGN_CLK(3);
         acc_phase ^= 1;
       }
-      if (fwd_only) continue;
-
+      if (!fwd_only) {
       // ---- pose columns, residual (thread = row; needs every d/d(input) column of the row) -----------
       epi_bar_sync();
       if (grp == 0) {
@@ -632,16 +656,16 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         jr[kMaxCode + 5] = x0 * g1 - x1 * g0;
         jr[kMaxCode + 6] = a.pose_only ? 0.f : (g0 * x0 + g1 * x1 + g2 * x2);
         jr[kMaxCode + 7] = 0.f;
-        float res = (a.mode == MODE_SDF) ? yv : res_in;
-        if (sc == 0.f && (a.mode == MODE_SDF || r >= nrows)) res = 0.f;
-        if (mask_out != nullptr && a.mode == MODE_SDF && r < nrows)
+        float res = (mode == MODE_SDF) ? yv : res_in;
+        if (sc == 0.f && (mode == MODE_SDF || r >= nrows)) res = 0.f;
+        if (mask_out != nullptr && mode == MODE_SDF && r < nrows)
           mask_out[M.pts_off + row0 + r] = (sc != 0.f && fabsf(res) <= 0.05f) ? 1 : 0;      // optimizer.py:76-78
-        S.rr[r] = huber_weight(fabsf(res), a.huber_b) * res;
-        S.rsc[r] = (a.mode == MODE_SDF) ? sc : (r < nrows ? 1.f : 0.f);
-        if (a.dbg_J != nullptr && o == a.dbg_obj && a.mode == MODE_SDF && r < nrows) a.dbg_res[row0 + r] = res;
+        S.rr[r] = huber_weight(fabsf(res), huber_b) * res;
+        S.rsc[r] = (mode == MODE_SDF) ? sc : (r < nrows ? 1.f : 0.f);
+        if (a.dbg_J != nullptr && o == a.dbg_obj && mode == MODE_SDF && r < nrows) a.dbg_res[row0 + r] = res;
       }
       epi_bar_sync();
-      if (a.dbg_J != nullptr && o == a.dbg_obj && a.mode == MODE_SDF) {
+      if (a.dbg_J != nullptr && o == a.dbg_obj && mode == MODE_SDF) {
         const int P = a.dbg_P, npose = a.pose_only ? 6 : 7;
         for (int idx = tid; idx < nrows * P; idx += kTcEpiThreads) {
           const int p = idx / P, c = idx - p * P;
@@ -650,7 +674,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         }
       }
       // ---- J^T J, J^T (rho r), loss over the 128 rows of the tile (optimizer.py:161-167) -------------
-      float* accp = a.part + (size_t)tile * kAccStride;
+      float* accp = part + (size_t)tile * kAccStride;
       if (tid < 171) {
         int bi = 0, rem = tid;
         while (rem >= 18 - bi) { rem -= 18 - bi; ++bi; }
@@ -696,14 +720,41 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         }
         if (k == 0) { accp[kAccLoss] = sacc; accp[kAccLoss + 1] = n; }
       }
+      }   // !fwd_only
       if (MEGA) {
-        // ---- object pipeline: the CTA that finishes an object's last tile solves its normal system, updates
-        // its pose/code and queues the tiles of its next iteration, while other objects keep the other SMs busy
-        __threadfence();                             // this tile's partial sums are visible device-wide
+        // ---- object pipeline.  Per object and iteration:  ray-sample tiles (forward only) -> [last one] per-ray scan +
+        // band compaction -> band tiles (fwd+bwd) ;  SDF tiles (fwd+bwd) ;  [last SDF / band tile] solve, pose / code
+        // update, tiles of the next iteration.  The CTA that finishes the last tile of a stage runs the serial step
+        // with its 256 epilogue threads while every other SM keeps working on other objects.
+        __threadfence();                             // this tile's partial sums / sdf values are visible device-wide
         epi_bar_sync();
-        if (tid == 0) *reinterpret_cast<volatile int*>(&S.last_flag) = (atomicSub(q.tiles_left + o, 1) == 1) ? 1 : 0;
+        if (tid == 0) {
+          int act = 0;
+          if (mode == MODE_RAYFWD) { if (atomicSub(q.ray_left + o, 1) == 1) act = 1; }
+          else if (atomicSub(q.pending + o, 1) == 1) act = 2;
+          *reinterpret_cast<volatile int*>(&S.last_flag) = act;
+        }
         epi_bar_sync();
-        if (*reinterpret_cast<volatile int*>(&S.last_flag)) {
+        int act = *reinterpret_cast<volatile int*>(&S.last_flag);
+        if (act == 1) {
+          // every ray sample of the object has its sdf value: occupancy scan, rendered depth, band rows (loss.py:84-141)
+          __threadfence();
+          scan_object<true>(sc_args, o, tid, kTcEpiThreads, reinterpret_cast<int*>(S.Jp), S.warp_tmp);
+          epi_bar_sync();
+          if (tid == 0) {
+            __threadfence();                         // band rows / band_m before the band tiles are published
+            const int m = ldv(sc_args.band_m + o);
+            const int ntB = (m + kTcRows - 1) / kTcRows;
+            // the render term's placeholder in `pending` becomes its ntB band tiles BEFORE they can be popped
+            atomicAdd(q.band_rows_total, m);
+            const int left = atomicAdd(q.pending + o, ntB - 1) + ntB - 1;
+            mega_push(q, MODE_BAND, o, ntB);
+            *reinterpret_cast<volatile int*>(&S.last_flag) = (left == 0) ? 2 : 0;
+          }
+          epi_bar_sync();
+          act = *reinterpret_cast<volatile int*>(&S.last_flag);
+        }
+        if (act == 2) {
           __threadfence();
           SolveSmem& SM = *reinterpret_cast<SolveSmem*>(S.Jp);
           const int it = ldv(q.obj_iter + o);
@@ -714,14 +765,14 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
             if (fin) {
               atomicAdd(q.done_objects, 1);
             } else {
-              const int nt = (M.n_pts + kTcRows - 1) / kTcRows;
+              const int ntS = (M.n_pts + kTcRows - 1) / kTcRows;
+              const int ntF = q.render ? (M.n_rays * a.D + kTcRows - 1) / kTcRows : 0;
               *reinterpret_cast<volatile int*>(q.obj_iter + o) = it + 1;
-              *reinterpret_cast<volatile int*>(q.tiles_left + o) = nt;
+              *reinterpret_cast<volatile int*>(q.pending + o) = ntS + (ntF > 0 ? 1 : 0);
+              *reinterpret_cast<volatile int*>(q.ray_left + o) = ntF;
               __threadfence();
-              const int base = atomicAdd(q.q_tail, nt);
-              for (int j = 0; j < nt; ++j) *reinterpret_cast<volatile int*>(q.q_items + base + j) = (o << 16) | j;
-              __threadfence();
-              for (int j = 0; j < nt; ++j) *reinterpret_cast<volatile int*>(q.q_flag + base + j) = 1;
+              mega_push(q, MODE_RAYFWD, o, ntF);      // the long chain (rays -> scan -> band -> solve) first
+              mega_push(q, MODE_SDF, o, ntS);
             }
           }
         }
@@ -735,11 +786,12 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
-  tc_body<false>(a, MegaArgs{}, SolveArgs{});
+  tc_body<false>(a, MegaArgs{}, SolveArgs{}, ScanArgs{});
 }
-// persistent object-pipelined variant: all GN iterations of all objects in ONE launch (SDF term / pose-only)
-__global__ void __launch_bounds__(kTcThreads, 1) k_gn_persistent(TermArgs a, MegaArgs q, SolveArgs sv) {
-  tc_body<true>(a, q, sv);
+// persistent object-pipelined variant: all GN iterations of all objects in ONE launch (joint runs with or without the
+// render term, pose-only runs)
+__global__ void __launch_bounds__(kTcThreads, 1) k_gn_persistent(TermArgs a, MegaArgs q, SolveArgs sv, ScanArgs sc) {
+  tc_body<true>(a, q, sv, sc);
 }
 
 // ------------------------------------------------------------------------------------------------
