@@ -204,9 +204,9 @@ __device__ __forceinline__ void elim_bar() { asm volatile("bar.sync 2, 96;" ::: 
 
 // Shared-memory workspace of one solve (static in k_solve, carved from the J tile in the persistent kernel)
 struct SolveSmem {
-  float As[kPMax * kAsStride];                 // assembled augmented system [H | b]; later the rows of U
+  float As[kPMax * kAsStride];                 // assembled augmented system [H | b]
   float4 bcast[2][(kPMax + 1) / 4 + 1];        // pivot row + rhs broadcast (double buffered)
-  float ys[kPMax], rdiag[kPMax], xs[kPMax];
+  float xs[kPMax];
   float s_rot[4];                              // J_rot.x, J_rot.z, res_rot, active
   double s_sum[4];                             // sdf loss sum, sdf rows, render loss sum
   int s_flag;
@@ -228,7 +228,7 @@ template <bool MEGA>
 __device__ int solve_object(const SolveArgs& a, const int o, const int tid, SolveSmem& SM, const bool last_iter) {
   float (&As)[kPMax * kAsStride] = SM.As;
   float4 (&bcast)[2][(kPMax + 1) / 4 + 1] = SM.bcast;
-  float (&ys)[kPMax] = SM.ys; float (&rdiag)[kPMax] = SM.rdiag; float (&xs)[kPMax] = SM.xs;
+  float (&xs)[kPMax] = SM.xs;
   float (&s_rot)[4] = SM.s_rot; double (&s_sum)[4] = SM.s_sum; int& s_flag = SM.s_flag;
   ObjState& st = a.state[o];
   const SolverParams& prm = a.prm;
@@ -339,16 +339,31 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
     accv[q] = 0.0; accr[q] = 0.0;
   }
   // tile partials summed in tile order; the thread's (up to 11) entries give 11 independent loads per tile
-  for (int t = 0; t < ntS; ++t) {
-    const float* pt = pS + (size_t)t * kAccStride;
+  // (four tiles' loads are issued before their sums: 44 independent L2 round trips in flight per thread; the
+  //  summation order -- tile 0, 1, 2, ... -- is unchanged)
+  auto sum_tiles = [&](const float* base, int nt, double (&acc)[kMaxEnt]) {
+    int t = 0;
+    for (; t + 4 <= nt; t += 4) {
+      float v[4][kMaxEnt];
 #pragma unroll
-    for (int q = 0; q < kMaxEnt; ++q) if (ei[q] >= 0) accv[q] += (double)__ldcg(pt + eidx[q]);
-  }
-  for (int t = 0; t < ntR; ++t) {
-    const float* pt = pR + (size_t)t * kAccStride;
+      for (int u = 0; u < 4; ++u) {
+        const float* pt = base + (size_t)(t + u) * kAccStride;
 #pragma unroll
-    for (int q = 0; q < kMaxEnt; ++q) if (ei[q] >= 0) accr[q] += (double)__ldcg(pt + eidx[q]);
-  }
+        for (int q = 0; q < kMaxEnt; ++q) v[u][q] = (ei[q] >= 0) ? __ldcg(pt + eidx[q]) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < kMaxEnt; ++q) acc[q] += (double)v[u][q];
+    }
+    for (; t < nt; ++t) {
+      const float* pt = base + (size_t)t * kAccStride;
+#pragma unroll
+      for (int q = 0; q < kMaxEnt; ++q) if (ei[q] >= 0) acc[q] += (double)__ldcg(pt + eidx[q]);
+    }
+  };
+  sum_tiles(pS, ntS, accv);
+  if (ntR > 0) sum_tiles(pR, ntR, accr);
   SOLVE_CLK(3);
 #pragma unroll
   for (int q = 0; q < kMaxEnt; ++q) {
@@ -391,19 +406,20 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
   }
   solve_sync<MEGA>();
   SOLVE_CLK(4);
-  // ---- Gaussian elimination of the SPD system, thread i = row i in registers; one barrier per pivot --------
+  // ---- Gauss-Jordan elimination of the SPD system, thread i = row i in registers; one barrier per pivot ----------
   if (tid < kElimThreads) {
-    // Thread i keeps row i of H in registers, rotated so that the current pivot column is always index 0:
-    // after pivot k, arow[j] holds H'[i][k+1+j].  The pivot loop stays rolled (small, cache-resident code)
-    // while every register index is a compile-time constant.  The broadcast pivot rows are the rows of U;
-    // they are parked in As (all rows were loaded into registers before the first barrier) for the
-    // back-substitution.
+    // Thread i keeps row i of [H | b] in registers, rotated so that the current pivot column is always index 0: after
+    // pivot k, arow[j] holds H'[i][k+1+j].  The pivot loop stays rolled (small, cache-resident code) while every register
+    // index is a compile-time constant.  Rows ABOVE the pivot are eliminated too (Jordan), so the system ends diagonal
+    // and x_i = b'_i / H'_ii with the diagonal each thread saved when its own row was the pivot: no U factor in shared
+    // memory and no back-substitution chain (71 more dependent barrier steps in the previous version).
     float arow[kPMax + 1];
     const int row = (tid < kPMax) ? tid : kPMax - 1;        // lanes 71..95 mirror the last row (results unused)
 #pragma unroll
     for (int j = 0; j < kPMax; ++j) arow[j] = As[row * kAsStride + j];
     arow[kPMax] = 0.f;
     float brow = As[row * kAsStride + kPMax];
+    float mydiag = 1.f;
     int bad_pivot = 0;
 #pragma unroll 1
     for (int k = 0; k < kPMax; ++k) {
@@ -412,6 +428,7 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
 #pragma unroll
         for (int j = 0; j <= kPMax; j += 4) buf[j >> 2] = make_float4(arow[j], arow[j + 1], arow[j + 2], arow[j + 3]);
         buf[(kPMax + 1) / 4] = make_float4(brow, 0.f, 0.f, 0.f);
+        mydiag = arow[0];
       }
       elim_bar();
       float pr[kPMax + 1];
@@ -423,26 +440,12 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
       const float pb = buf[(kPMax + 1) / 4].x;
       const float piv = pr[0];
       if (!(piv > 0.f) || !(piv < 3.0e38f)) bad_pivot = 1;        // every thread sees the same pivot
-      const float rpiv = __frcp_rn(piv);
-      // U[k][k + t] = pivot_row[t] (t < 71 - k), y_k = pb
-      if (tid < kPMax - k) As[k * kAsStride + k + tid] = reinterpret_cast<const float*>(buf)[tid];
-      if (tid == kElimThreads - 1) { ys[k] = pb; rdiag[k] = rpiv; }
-      if (tid > k) {
-        const float l = arow[0] * rpiv;
+      const float l = (tid == k) ? 0.f : arow[0] * __frcp_rn(piv);
 #pragma unroll
-        for (int j = 1; j <= kPMax; ++j) arow[j - 1] = fmaf(-l, pr[j], arow[j]);
-        brow = fmaf(-l, pb, brow);
-      }
+      for (int j = 1; j <= kPMax; ++j) arow[j - 1] = fmaf(-l, pr[j], arow[j]);
+      brow = fmaf(-l, pb, brow);
     }
-    elim_bar();
-    // ---- back substitution  U x = y, column oriented, U and y in shared memory ----------------------------
-    float yreg = (tid < kPMax) ? ys[tid] : 0.f;
-#pragma unroll 1
-    for (int j = kPMax - 1; j >= 0; --j) {
-      if (tid == j) xs[j] = yreg * rdiag[j];
-      elim_bar();
-      if (tid < j) yreg = fmaf(-As[tid * kAsStride + j], xs[j], yreg);
-    }
+    if (tid < kPMax) xs[tid] = brow / mydiag;
     if (bad_pivot && tid == 0) s_flag = 1;
   }
   solve_sync<MEGA>();
