@@ -18,6 +18,8 @@ using namespace dspgn;
 
 namespace {
 
+constexpr int kEvCap = 1 << 18;     // events of the persistent kernel's debug log (env DSPGN_CLK)
+
 thread_local std::string g_err;
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -100,7 +102,7 @@ struct DspgnSolver {
   long long total_ray_tiles128 = 0;// ray-sample tiles of the batch
   int max_tiles128 = 0;            // largest tile count of one term of one object (queue items hold 19 bits)
   bool mega_enabled = true;
-  DevBuf d_clk;
+  DevBuf d_clk, d_ev, d_seg;
   bool clk_on = false;
   HostBuf h_results;
   // counters
@@ -303,7 +305,7 @@ void dspgn_solver_destroy(DspgnSolver* s) {
   dspgn_gather_close(s);
   for (DevBuf* b : {&s->d_decs, &s->d_stage, &s->d_state, &s->d_part_s, &s->d_part_r, &s->d_tbase, &s->d_V, &s->d_m, &s->d_results, &s->d_active,
                     &s->d_sdf, &s->d_bx, &s->d_bs, &s->d_br, &s->d_dbg, &s->d_clk, &s->d_q_items, &s->d_q_flag, &s->d_q_ctr,
-                    &s->d_tiles_left, &s->d_obj_iter}) b->release();
+                    &s->d_tiles_left, &s->d_obj_iter, &s->d_ev, &s->d_seg}) b->release();
   s->h_stage.release();
   s->h_results.release();
   for (auto e : s->ev) cudaEventDestroy(e);
@@ -626,7 +628,8 @@ int run_batch_impl(DspgnSolver* s, int mode) {
   CU(cudaEventRecord(s->ev_run0, s->stream));
   const bool render = !pose_only && !s->cfg.sdf_only;
   // queue capacity: per iteration every SDF tile, every ray-sample tile and at most as many band tiles again
-  const long long items_per_iter = (long long)s->total_tiles128 + (render ? 2 * s->total_ray_tiles128 : 0);
+  const long long items_per_iter = (long long)s->total_tiles128 +
+                                   (render ? 2 * s->total_ray_tiles128 + s->tot_rays / kScanChunkRays + s->n_obj : 0);
   const bool mega = s->mega_enabled && s->engine == DSPGN_ENGINE_TC && s->total_tiles128 > 0 &&
                     s->max_tiles128 <= kItemTileMask && s->n_obj <= kItemObjMask + 1 && items_per_iter * iters < (1LL << 27);
   if (mega) {
@@ -636,7 +639,9 @@ int run_batch_impl(DspgnSolver* s, int mode) {
     bad |= s->d_q_items.reserve(4 * (size_t)cap);
     bad |= s->d_q_flag.reserve(4 * (size_t)cap);
     bad |= s->d_q_ctr.reserve(4 * 128);
-    bad |= s->d_tiles_left.reserve(4 * 2 * (size_t)s->n_obj);
+    bad |= s->d_tiles_left.reserve(4 * 3 * (size_t)s->n_obj);
+    const size_t nseg_cap = (size_t)s->tot_rays / kSegRays + s->n_obj + 2;
+    if (render) bad |= s->d_seg.reserve(4 * 2 * nseg_cap);
     bad |= s->d_obj_iter.reserve(4 * (size_t)s->n_obj);
     if (bad) return fail(DSPGN_E_ALLOC, "queue allocation failed");
     CU(cudaMemsetAsync(s->d_q_flag.p, 0, 4 * (size_t)cap, s->stream));
@@ -655,6 +660,13 @@ int run_batch_impl(DspgnSolver* s, int mode) {
     q.q_head = s->d_q_ctr.as<int>(); q.q_tail = s->d_q_ctr.as<int>() + 32; q.done_objects = s->d_q_ctr.as<int>() + 64;
     q.band_rows_total = s->d_q_ctr.as<int>() + 80;
     q.pending = s->d_tiles_left.as<int>(); q.ray_left = s->d_tiles_left.as<int>() + s->n_obj; q.obj_iter = s->d_obj_iter.as<int>();
+    q.scan_left = s->d_tiles_left.as<int>() + 2 * s->n_obj;
+    q.seg_cnt = s->d_seg.as<int>(); q.seg_prefix = s->d_seg.as<int>() + nseg_cap;
+    if (s->clk_on) {
+      if (s->d_ev.reserve(8 * (1 + 2 * (size_t)kEvCap))) return fail(DSPGN_E_ALLOC, "cudaMalloc");
+      CU(cudaMemsetAsync(s->d_ev.p, 0, 8, s->stream));
+      q.ev = s->d_ev.as<long long>(); q.ev_cap = kEvCap;
+    }
     SolveArgs v = base_solve(s, pose_only);
     v.base_s = s->d_tbase_static; v.base_r = s->d_tbase_r_static; v.tile_rows = kTcRows; v.last_iter = 0; v.iter_index = 0; v.dbg_clk = nullptr;
     ScanArgs sa = base_scan(s);
@@ -996,6 +1008,21 @@ int dspgn_debug_clocks(DspgnSolver* s, long long* out, int n) {
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaMemcpy(out, s->d_clk.p, sizeof(long long) * (size_t)std::min(n, have), cudaMemcpyDeviceToHost));
   return 0;
+}
+
+int dspgn_debug_events(DspgnSolver* s, long long* out, int max_events) {
+  // event log of the last persistent-kernel run (env DSPGN_CLK=1 at solver creation): returns the number of events,
+  // out[2*i] = %globaltimer (ns), out[2*i+1] = kind<<56 | mode<<52 | sm<<40 | object<<24 | tile (or iteration)
+  if (!s || !out || max_events < 1) return fail(DSPGN_E_ARG, "bad argument");
+  if (!s->clk_on || !s->d_ev.p) return fail(DSPGN_E_ARG, "event log not enabled (DSPGN_CLK)");
+  CU(cudaSetDevice(s->device));
+  CU(cudaStreamSynchronize(s->stream));
+  long long n = 0;
+  CU(cudaMemcpy(&n, s->d_ev.p, 8, cudaMemcpyDeviceToHost));
+  if (n > kEvCap) n = kEvCap;
+  if (n > max_events) n = max_events;
+  CU(cudaMemcpy(out, s->d_ev.as<long long>() + 1, 16 * (size_t)n, cudaMemcpyDeviceToHost));
+  return (int)n;
 }
 
 int dspgn_tc_selftest(int device, int n_mma, int k_steps, const float* A, const float* B, float* D) {

@@ -63,6 +63,7 @@ struct TermArgs {
 // Device work queue of the persistent object-pipelined kernel (dspgn_tc.cuh).
 // item = kind << 29 | object << 19 | tile   (kind: the tile's MODE_*; object < 1024; tile < 2^19; always >= 0)
 constexpr int kItemKindShift = 29, kItemObjShift = 19, kItemTileMask = (1 << 19) - 1, kItemObjMask = 1023;
+constexpr int kKindScan = 3;   // queue-only kind: per-ray scan of a 64-ray chunk (no GEMM steps); 0..2 = MODE_SDF / MODE_BAND / MODE_RAYFWD
 __host__ __device__ __forceinline__ int make_item(int kind, int o, int tile) {
   return (kind << kItemKindShift) | (o << kItemObjShift) | tile;
 }
@@ -75,10 +76,25 @@ struct MegaArgs {
   int* pending;              // [n_obj] SDF + band tiles of the object's current iteration still running (+1 while the
                              //         render term has not been expanded into band tiles yet)
   int* ray_left;             // [n_obj] ray-sample tiles of the current iteration still running
+  int* scan_left;            // [n_obj] scan items (64-ray chunks) of the current iteration still running
+  int* seg_cnt; int* seg_prefix;   // band rows kept per 8-ray segment / their exclusive prefix per object (dspgn_solve.cuh)
   int* obj_iter;             // [n_obj] current iteration of each object
   int* done_objects;         // objects finished (last iteration or frozen)
   int* band_rows_total;      // sum of band rows over all objects and iterations (roofline accounting)
+  long long* ev; int ev_cap; // optional event log (env DSPGN_CLK): ev[0] = count, then {globaltimer ns, kind<<48|sm<<32|o<<20|tile}
 };
+// event kinds of the persistent kernel's debug log
+enum { EV_TILE_BEGIN = 0, EV_TILE_END = 1, EV_SCAN_BEGIN = 2, EV_SCAN_END = 3, EV_SOLVE_BEGIN = 4, EV_SOLVE_END = 5, EV_POPPED = 6, EV_FIRST_MMA = 7 };
+__device__ __forceinline__ void mega_event(const MegaArgs& q, int kind, int mode, int o, int tile) {
+  if (q.ev == nullptr) return;
+  const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(q.ev), 1ull);
+  if ((long long)slot >= q.ev_cap) return;
+  unsigned long long t; unsigned sm;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+  q.ev[1 + 2 * slot] = (long long)t;
+  q.ev[2 + 2 * slot] = ((long long)kind << 56) | ((long long)mode << 52) | ((long long)sm << 40) | ((long long)o << 24) | (long long)tile;
+}
 
 // ---------------------------------------------------------------------------------------------
 // tile scheduling shared by all decoder kernels: rows per object -> tiles, scanned per CTA

@@ -423,10 +423,14 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
     int bad_pivot = 0;
 #pragma unroll 1
     for (int k = 0; k < kPMax; ++k) {
+      // after k rotations only entries 0 .. 71-k of a rotated row can be non-zero: the (warp-uniform) tail of every
+      // broadcast / load / update loop is skipped, which halves the shared-memory traffic and the FMA chain on average
+      const int live = kPMax + 1 - k;                              // entries [0, live) matter (entry `live-1` is the zero pad at k = 0)
       float4* buf = bcast[k & 1];
       if (tid == k) {
 #pragma unroll
-        for (int j = 0; j <= kPMax; j += 4) buf[j >> 2] = make_float4(arow[j], arow[j + 1], arow[j + 2], arow[j + 3]);
+        for (int j = 0; j <= kPMax; j += 4)
+          if (j < live) buf[j >> 2] = make_float4(arow[j], arow[j + 1], arow[j + 2], arow[j + 3]);
         buf[(kPMax + 1) / 4] = make_float4(brow, 0.f, 0.f, 0.f);
         mydiag = arow[0];
       }
@@ -434,15 +438,28 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
       float pr[kPMax + 1];
 #pragma unroll
       for (int j = 0; j <= kPMax; j += 4) {
-        const float4 v = buf[j >> 2];
-        pr[j] = v.x; pr[j + 1] = v.y; pr[j + 2] = v.z; pr[j + 3] = v.w;
+        if (j < live) {
+          const float4 v = buf[j >> 2];
+          pr[j] = v.x; pr[j + 1] = v.y; pr[j + 2] = v.z; pr[j + 3] = v.w;
+        } else {
+          pr[j] = 0.f; pr[j + 1] = 0.f; pr[j + 2] = 0.f; pr[j + 3] = 0.f;
+        }
       }
       const float pb = buf[(kPMax + 1) / 4].x;
       const float piv = pr[0];
       if (!(piv > 0.f) || !(piv < 3.0e38f)) bad_pivot = 1;        // every thread sees the same pivot
       const float l = (tid == k) ? 0.f : arow[0] * __frcp_rn(piv);
 #pragma unroll
-      for (int j = 1; j <= kPMax; ++j) arow[j - 1] = fmaf(-l, pr[j], arow[j]);
+      for (int j = 0; j <= kPMax; j += 4) {
+        if (j < live) {
+          if (j > 0) arow[j - 1] = fmaf(-l, pr[j], arow[j]);
+          arow[j] = fmaf(-l, pr[j + 1], arow[j + 1]);
+          arow[j + 1] = fmaf(-l, pr[j + 2], arow[j + 2]);
+          if (j + 3 <= kPMax) arow[j + 2] = fmaf(-l, pr[j + 3], arow[j + 3]);
+        } else if (j > 0 && j - 4 < live) {
+          arow[j - 1] = 0.f;                                       // the entry that rotates in behind the live range
+        }
+      }
       brow = fmaf(-l, pb, brow);
     }
     if (tid < kPMax) xs[tid] = brow / mydiag;
@@ -517,16 +534,24 @@ __device__ __forceinline__ void load_scan_state(const ObjState& st, ScanState& c
   c.dmin = ldv(&st.dmin); c.dmax = ldv(&st.dmax); c.dstep = ldv(&st.dstep); c.dfar = ldv(&st.dfar);
 }
 
-__device__ __forceinline__ void ray_scan(const ScanArgs& a, const ObjMeta& M, const ScanState& st, int ray, int lane,
-                                         bool keep[2], float de_ds[2], float& res) {
-  const int D = a.D;
-  const float th = a.th;
-  const float* srow = a.sdf + (size_t)M.smp_off + (size_t)ray * D;
-  float s[2], o[2], q[2];
+// sdf values of one ray (lane = sample slot, two slots per lane); +inf beyond D / outside the unit sphere
+__device__ __forceinline__ void ray_load(const ScanArgs& a, const ObjMeta& M, int ray, int lane, float s[2]) {
+  const float* srow = a.sdf + (size_t)M.smp_off + (size_t)ray * a.D;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int j = lane + 32 * h;
-    s[h] = (j < D) ? __ldcg(srow + j) : INFINITY;    // written by other CTAs (L2 is the point of coherence)
+    s[h] = (j < a.D) ? __ldcg(srow + j) : INFINITY;  // written by other CTAs (L2 is the point of coherence)
+  }
+}
+
+__device__ __forceinline__ void ray_scan_vals(const ScanArgs& a, const ObjMeta& M, const ScanState& st, int ray, int lane,
+                                              const float s[2], bool keep[2], float de_ds[2], float& res) {
+  const int D = a.D;
+  const float th = a.th;
+  float o[2], q[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = lane + 32 * h;
     o[h] = (j < D) ? occupancy(s[h], th) : 0.f;      // +inf -> clamp -> 0 (outside sphere: loss.py:84)
     q[h] = 1.f - o[h];
   }
@@ -575,6 +600,91 @@ __device__ __forceinline__ void ray_scan(const ScanArgs& a, const ObjMeta& M, co
   res = fminf(fmaxf(dobs - du, -0.3f), 0.3f);           // loss.py:136-141
 }
 
+__device__ __forceinline__ void ray_scan(const ScanArgs& a, const ObjMeta& M, const ScanState& st, int ray, int lane,
+                                         bool keep[2], float de_ds[2], float& res) {
+  float s[2];
+  ray_load(a, M, ray, lane, s);
+  ray_scan_vals(a, M, st, ray, lane, s, keep, de_ds, res);
+}
+
+// write the kept samples of one ray as band rows (x_o, de/ds, residual) starting at row `base` (ray, sample order)
+__device__ __forceinline__ int ray_emit(const ScanArgs& a, const ObjMeta& M, const ScanState& st, int ray, int lane,
+                                        const bool keep[2], const float de_ds[2], float res, size_t base) {
+  const unsigned b0 = __ballot_sync(0xffffffffu, keep[0]), b1 = __ballot_sync(0xffffffffu, keep[1]);
+  const float* q = a.rays + 3 * (size_t)(M.ray_off + ray);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (!keep[h]) continue;
+    const int j = lane + 32 * h;
+    const int pos = (h == 0 ? __popc(b0 & ((1u << lane) - 1u)) : __popc(b0) + __popc(b1 & ((1u << lane) - 1u)));
+    const float d = lin_depth(st.dmin, st.dmax, st.dstep, j, a.D);
+    float x, y, z;
+    xform_point(st.T, __fmul_rn(q[0], d), __fmul_rn(q[1], d), __fmul_rn(q[2], d), x, y, z);
+    const size_t row = base + pos;
+    a.band_x[3 * row] = x; a.band_x[3 * row + 1] = y; a.band_x[3 * row + 2] = z;
+    a.band_s[row] = de_ds[h];
+    a.band_r[row] = res;
+  }
+  return __popc(b0) + __popc(b1);
+}
+
+// ---- persistent kernel: the scan as parallel work items --------------------------------------------------------------
+// A scan item covers kScanChunkRays consecutive rays of one object; warp w of the CTA's 8 epilogue warps owns the
+// "segment" of kSegRays rays  [chunk*64 + 8w, +8)  and writes its kept rows compactly at the START of the segment's own
+// sample range (single pass, all sdf loads of the segment issued up front).  Band rows keep the global (ray, sample)
+// order; band tiles find them through the per-object exclusive prefix over the segment counts.
+constexpr int kSegRays = 8, kScanChunkRays = 64;
+__device__ __forceinline__ int seg_base(const ObjMeta& M, int o) { return M.ray_off / kSegRays + o; }   // first segment slot of object o
+
+__device__ inline void scan_chunk(const ScanArgs& a, int* seg_cnt, const int o, const int chunk, const int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const ObjMeta M = a.meta[o];
+  const int seg = chunk * (kScanChunkRays / kSegRays) + warp;
+  const int ray0 = seg * kSegRays;
+  if (ray0 >= M.n_rays) return;
+  ScanState st;
+  load_scan_state(a.state[o], st);
+  float sv[kSegRays][2];
+#pragma unroll
+  for (int i = 0; i < kSegRays; ++i) {
+    if (ray0 + i < M.n_rays) ray_load(a, M, ray0 + i, lane, sv[i]);
+    else { sv[i][0] = INFINITY; sv[i][1] = INFINITY; }
+  }
+  int count = 0;
+  const size_t base = (size_t)M.smp_off + (size_t)ray0 * a.D;
+#pragma unroll
+  for (int i = 0; i < kSegRays; ++i) {
+    if (ray0 + i >= M.n_rays) break;                       // warp-uniform
+    bool keep[2]; float de_ds[2]; float res;
+    ray_scan_vals(a, M, st, ray0 + i, lane, sv[i], keep, de_ds, res);
+    count += ray_emit(a, M, st, ray0 + i, lane, keep, de_ds, res, base + count);
+  }
+  if (lane == 0) seg_cnt[seg_base(M, o) + seg] = count;
+}
+
+// exclusive prefix over the object's segment counts -> seg_prefix[0..nseg], band_m[o] = total.  256 threads, named barrier 1.
+__device__ inline void scan_prefix(const ScanArgs& a, const int* seg_cnt, int* seg_prefix, const int o, const int tid, int* s_wsum) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const ObjMeta M = a.meta[o];
+  const int nseg = (M.n_rays + kSegRays - 1) / kSegRays, sb = seg_base(M, o);
+  int carry = 0;
+  for (int b0 = 0; b0 < nseg; b0 += 256) {
+    const int i = b0 + tid;
+    const int v = (i < nseg) ? __ldcg(seg_cnt + sb + i) : 0;
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) s_wsum[warp] = x;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    int woff = 0, tot = 0;
+    for (int w = 0; w < 8; ++w) { if (w < warp) woff += s_wsum[w]; tot += s_wsum[w]; }
+    if (i < nseg) seg_prefix[sb + i] = carry + woff + x - v;
+    carry += tot;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+  }
+  if (tid == 0) { seg_prefix[sb + nseg] = carry; a.band_m[o] = carry; }
+}
+
 // The per-object scan: called by all `nthreads` threads of k_ray_scan's CTA (MEGA = false) or by the 256 epilogue
 // threads of the persistent kernel's CTA that finished the object's last ray-sample tile (MEGA = true).
 // s_cnt: kScanMaxRays ints, s_wsum: 32 ints of shared memory.
@@ -616,22 +726,7 @@ __device__ inline void scan_object(const ScanArgs& a, const int o, const int tid
   if (tid == 0) a.band_m[o] = carry;
   for (int ray = warp; ray < N; ray += nw) {
     ray_scan(a, M, st, ray, lane, keep, de_ds, res);
-    const unsigned b0 = __ballot_sync(0xffffffffu, keep[0]), b1 = __ballot_sync(0xffffffffu, keep[1]);
-    const int base = s_cnt[ray];
-    const float* q = a.rays + 3 * (size_t)(M.ray_off + ray);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (!keep[h]) continue;
-      const int j = lane + 32 * h;
-      const int pos = base + (h == 0 ? __popc(b0 & ((1u << lane) - 1u)) : __popc(b0) + __popc(b1 & ((1u << lane) - 1u)));
-      const float d = lin_depth(st.dmin, st.dmax, st.dstep, j, a.D);
-      float x, y, z;
-      xform_point(st.T, __fmul_rn(q[0], d), __fmul_rn(q[1], d), __fmul_rn(q[2], d), x, y, z);
-      const size_t row = (size_t)M.smp_off + pos;
-      a.band_x[3 * row] = x; a.band_x[3 * row + 1] = y; a.band_x[3 * row + 2] = z;
-      a.band_s[row] = de_ds[h];
-      a.band_r[row] = res;
-    }
+    ray_emit(a, M, st, ray, lane, keep, de_ds, res, (size_t)M.smp_off + s_cnt[ray]);
   }
 }
 

@@ -289,6 +289,35 @@ __device__ inline void mega_push(const MegaArgs& q, int kind, int o, int n) {
   for (int j = 0; j < n; ++j) *reinterpret_cast<volatile int*>(q.q_flag + base + j) = 1;
 }
 
+// all terms of the object's current iteration are in: solve, update, queue the next iteration (or finish).  Called by
+// the 256 epilogue threads of the CTA that completed the object's last outstanding tile.
+template <bool MEGA>
+__device__ __noinline__ void mega_solve_and_advance(const TermArgs& a, const MegaArgs& q, const SolveArgs& sv, TcSmemTail& S, int o, int tid) {
+  __threadfence();
+  SolveSmem& SM = *reinterpret_cast<SolveSmem*>(S.Jp);
+  const int it = ldv(q.obj_iter + o);
+  if (tid == 0) mega_event(q, EV_SOLVE_BEGIN, 0, o, it);
+  const int fin = solve_object<true>(sv, o, tid, SM, it + 1 >= q.n_iters);
+  epi_bar_sync();
+  if (tid == 0) {
+    mega_event(q, EV_SOLVE_END, 0, o, it);
+    __threadfence();                         // state / result record before anything is published
+    if (fin) {
+      atomicAdd(q.done_objects, 1);
+    } else {
+      const ObjMeta M = a.meta[o];
+      const int ntS = (M.n_pts + kTcRows - 1) / kTcRows;
+      const int ntF = q.render ? (M.n_rays * a.D + kTcRows - 1) / kTcRows : 0;
+      *reinterpret_cast<volatile int*>(q.obj_iter + o) = it + 1;
+      *reinterpret_cast<volatile int*>(q.pending + o) = ntS + (ntF > 0 ? 1 : 0);
+      *reinterpret_cast<volatile int*>(q.ray_left + o) = ntF;
+      __threadfence();
+      mega_push(q, MODE_RAYFWD, o, ntF);      // the long chain (rays -> scan -> band -> solve) first
+      mega_push(q, MODE_SDF, o, ntS);
+    }
+  }
+}
+
 template <bool MEGA>
 __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, const SolveArgs& sv, const ScanArgs& sc_args) {
   extern __shared__ unsigned char tc_smem_raw[];
@@ -328,6 +357,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
           volatile int* es = &S.epi_seq;
           for (unsigned spins = 0; seq - *es >= 3; ++spins) { __nanosleep(64); if (spins > (1u << 26)) __trap(); }
           const int item = mega_pop(q, a.n_obj);
+          if (item >= 0) mega_event(q, EV_POPPED, item >> kItemKindShift, (item >> kItemObjShift) & kItemObjMask, item & kItemTileMask);
           reinterpret_cast<volatile int*>(S.fifo)[seq & 3] = item;
           __threadfence_block();
           *reinterpret_cast<volatile int*>(&S.fifo_pub) = seq + 1;
@@ -339,7 +369,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         const TcPlan& plan = S.plans[cls];
         const unsigned char* blob = a.decs[cls].tc_blob;
         const bool fwd_only = (tr.mode == MODE_RAYFWD || tr.mode == MODE_PTSFWD);
-        const int ns = fwd_only ? plan.n_fwd : plan.n_steps;
+        const int ns = (MEGA && tr.mode == kKindScan) ? 0 : (fwd_only ? plan.n_fwd : plan.n_steps);
         for (int s = 0; s < ns; ++s) {
           const TcStep st = plan.step[s];
           const uint32_t img = (uint32_t)st.n_mma * 128u;
@@ -368,7 +398,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
       const int o = tr.o;
       const TcPlan& plan = S.plans[a.meta[o].class_id];
       const bool fwd_only = (tr.mode == MODE_RAYFWD || tr.mode == MODE_PTSFWD);
-      const int ns = fwd_only ? plan.n_fwd : plan.n_steps;
+      const int ns = (MEGA && tr.mode == kKindScan) ? 0 : (fwd_only ? plan.n_fwd : plan.n_steps);
       for (int s = 0; s < ns; ++s) {
         const TcStep st = plan.step[s];
         const uint32_t d_t = tmem + (uint32_t)st.d_reg * 256u;
@@ -385,6 +415,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
           mbar_wait(&S.a_ready[2 * c + 1], ar_phase);
           if (last)
             for (int u = 2 * c + 2; u < 8; ++u) mbar_wait(&S.a_ready[u], ar_phase);
+          if (MEGA && c == 0 && s == 0 && lane == 0) mega_event(q, EV_FIRST_MMA, tr.mode, tr.o, tr.tile);
           if (c == 0 && lane == 0) {
             DSPGN_CLK(4);
             if (a.dbg_clk != nullptr && blockIdx.x == 0 && clk_tile < kClkTiles) {
@@ -433,7 +464,40 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
       ++clk_tile;
       TileRef tr;
       if (!tile_at<MEGA>(a, S, seq, total_tiles, tr)) break;
-      if (MEGA && tid == 0) *reinterpret_cast<volatile int*>(&S.epi_seq) = seq + 1;
+      if (MEGA && tid == 0) { *reinterpret_cast<volatile int*>(&S.epi_seq) = seq + 1; mega_event(q, EV_TILE_BEGIN, tr.mode, tr.o, tr.tile); }
+      if (MEGA && tr.mode == kKindScan) {
+        // ---- scan item: occupancy scan / rendered depth / band rows of 64 rays (loss.py:84-141); no GEMM steps ----------
+        const int o = tr.o;
+        scan_chunk(sc_args, q.seg_cnt, o, tr.tile, tid);
+        __threadfence();
+        epi_bar_sync();
+        if (tid == 0) {
+          mega_event(q, EV_TILE_END, tr.mode, o, tr.tile);
+          *reinterpret_cast<volatile int*>(&S.last_flag) = (atomicSub(q.scan_left + o, 1) == 1) ? 1 : 0;
+        }
+        epi_bar_sync();
+        int act = *reinterpret_cast<volatile int*>(&S.last_flag);
+        if (act == 1) {
+          // last chunk of the object: segment prefix -> band row count -> band tiles
+          __threadfence();
+          scan_prefix(sc_args, q.seg_cnt, q.seg_prefix, o, tid, S.warp_tmp);
+          epi_bar_sync();
+          if (tid == 0) {
+            __threadfence();                         // prefix / band_m / band rows before the band tiles are published
+            const int m = ldv(sc_args.band_m + o);
+            const int ntB = (m + kTcRows - 1) / kTcRows;
+            atomicAdd(q.band_rows_total, m);
+            // the render term's placeholder in `pending` becomes its ntB band tiles BEFORE they can be popped
+            const int left = atomicAdd(q.pending + o, ntB - 1) + ntB - 1;
+            mega_push(q, MODE_BAND, o, ntB);
+            *reinterpret_cast<volatile int*>(&S.last_flag) = (left == 0) ? 2 : 0;
+          }
+          epi_bar_sync();
+          act = *reinterpret_cast<volatile int*>(&S.last_flag);
+        } else act = 0;
+        if (act == 2) mega_solve_and_advance<MEGA>(a, q, sv, S, o, tid);
+        continue;
+      }
       const int o = tr.o, row0 = tr.row0, tile = tr.slot, mode = tr.mode;
       const ObjMeta M = a.meta[o];
       const ObjState& ost = a.state[o];
@@ -465,6 +529,17 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         mask_in = (it_now > a.cut_iter) ? a.pt_active_out : nullptr;
         mask_out = (it_now == a.cut_iter) ? a.pt_active_out : nullptr;
       }
+      const int* segp = nullptr;
+      int nseg = 0;
+      if (MEGA && mode == MODE_BAND) {
+        // band rows live compacted per 8-ray segment: stage the object's segment prefix (<= 1025 ints) in the idle J tile
+        nseg = (M.n_rays + kSegRays - 1) / kSegRays;
+        int* sp = reinterpret_cast<int*>(S.Jp);
+        const int* gp = q.seg_prefix + seg_base(M, o);
+        for (int i = tid; i <= nseg; i += kTcEpiThreads) sp[i] = __ldcg(gp + i);
+        epi_bar_sync();
+        segp = sp;
+      }
       float x0 = 0.f, x1 = 0.f, x2 = 0.f, sc = 0.f, res_in = 0.f;
       if (r < nrows) {
         const int rr_ = row0 + r;
@@ -473,8 +548,13 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
           xform_point(Toc, q[0], q[1], q[2], x0, x1, x2);
           sc = (mask_in == nullptr || ldv(mask_in + M.pts_off + rr_)) ? 1.f : 0.f;
         } else if (mode == MODE_BAND) {
-          // band rows were written by the CTA that ran this object's scan: L2 is the point of coherence
-          const size_t sidx = (size_t)M.smp_off + rr_;
+          // band rows were written by the CTAs that ran this object's scan: L2 is the point of coherence
+          size_t sidx = (size_t)M.smp_off + rr_;
+          if (MEGA) {
+            int lo = 0, hi = nseg;                     // largest segment with prefix <= row
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (segp[mid] <= rr_) lo = mid; else hi = mid; }
+            sidx = (size_t)M.smp_off + (size_t)lo * kSegRays * a.D + (size_t)(rr_ - segp[lo]);
+          }
           x0 = __ldcg(a.band_x + 3 * sidx); x1 = __ldcg(a.band_x + 3 * sidx + 1); x2 = __ldcg(a.band_x + 3 * sidx + 2);
           sc = __ldcg(a.band_s + sidx); res_in = __ldcg(a.band_r + sidx);
         } else {
@@ -729,6 +809,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         __threadfence();                             // this tile's partial sums / sdf values are visible device-wide
         epi_bar_sync();
         if (tid == 0) {
+          mega_event(q, EV_TILE_END, mode, o, tr.tile);
           int act = 0;
           if (mode == MODE_RAYFWD) { if (atomicSub(q.ray_left + o, 1) == 1) act = 1; }
           else if (atomicSub(q.pending + o, 1) == 1) act = 2;
@@ -737,45 +818,15 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         epi_bar_sync();
         int act = *reinterpret_cast<volatile int*>(&S.last_flag);
         if (act == 1) {
-          // every ray sample of the object has its sdf value: occupancy scan, rendered depth, band rows (loss.py:84-141)
-          __threadfence();
-          scan_object<true>(sc_args, o, tid, kTcEpiThreads, reinterpret_cast<int*>(S.Jp), S.warp_tmp);
-          epi_bar_sync();
+          // every ray sample of the object has its sdf value: the per-ray scan becomes 64-ray work items of its own
           if (tid == 0) {
-            __threadfence();                         // band rows / band_m before the band tiles are published
-            const int m = ldv(sc_args.band_m + o);
-            const int ntB = (m + kTcRows - 1) / kTcRows;
-            // the render term's placeholder in `pending` becomes its ntB band tiles BEFORE they can be popped
-            atomicAdd(q.band_rows_total, m);
-            const int left = atomicAdd(q.pending + o, ntB - 1) + ntB - 1;
-            mega_push(q, MODE_BAND, o, ntB);
-            *reinterpret_cast<volatile int*>(&S.last_flag) = (left == 0) ? 2 : 0;
-          }
-          epi_bar_sync();
-          act = *reinterpret_cast<volatile int*>(&S.last_flag);
-        }
-        if (act == 2) {
-          __threadfence();
-          SolveSmem& SM = *reinterpret_cast<SolveSmem*>(S.Jp);
-          const int it = ldv(q.obj_iter + o);
-          const int fin = solve_object<true>(sv, o, tid, SM, it + 1 >= q.n_iters);
-          epi_bar_sync();
-          if (tid == 0) {
-            __threadfence();                         // state / result record before anything is published
-            if (fin) {
-              atomicAdd(q.done_objects, 1);
-            } else {
-              const int ntS = (M.n_pts + kTcRows - 1) / kTcRows;
-              const int ntF = q.render ? (M.n_rays * a.D + kTcRows - 1) / kTcRows : 0;
-              *reinterpret_cast<volatile int*>(q.obj_iter + o) = it + 1;
-              *reinterpret_cast<volatile int*>(q.pending + o) = ntS + (ntF > 0 ? 1 : 0);
-              *reinterpret_cast<volatile int*>(q.ray_left + o) = ntF;
-              __threadfence();
-              mega_push(q, MODE_RAYFWD, o, ntF);      // the long chain (rays -> scan -> band -> solve) first
-              mega_push(q, MODE_SDF, o, ntS);
-            }
+            const int nch = (M.n_rays + kScanChunkRays - 1) / kScanChunkRays;
+            *reinterpret_cast<volatile int*>(q.scan_left + o) = nch;
+            __threadfence();
+            mega_push(q, kKindScan, o, nch);
           }
         }
+        if (act == 2) mega_solve_and_advance<MEGA>(a, q, sv, S, o, tid);
       }
       // the next tile's prologue starts with epi_bar_sync(): Jp / rr are not rewritten before it
     }

@@ -207,6 +207,10 @@ int dspgn_debug_system_iter(DspgnSolver* s, int obj, int mode, int iter, float* 
  * (only when the solver was created with env DSPGN_CLK set). */
 int dspgn_debug_clocks(DspgnSolver* s, long long* out, int n);
 
+/* Debug: event log of the last persistent-kernel run (tile begin/end per kind, scan, solve, queue pops), enabled by
+ * env DSPGN_CLK at solver creation; returns the number of (timestamp, descriptor) pairs written, or a negative code. */
+int dspgn_debug_events(DspgnSolver* s, long long* out, int max_events);
+
 /* Test hook for the tcgen05 operand paths: D[128][n_mma] = A[128][16*k_steps] * B[n_mma][16*k_steps]^T
  * (A through the TMEM split-fp16 path, B through the pre-swizzled shared-memory images). Host buffers. */
 int dspgn_tc_selftest(int device, int n_mma, int k_steps, const float* A, const float* B, float* D);
