@@ -22,7 +22,9 @@ LIB_PATH = os.path.join(_HERE, "libdspgn.so")
 class DecoderSpec(C.Structure):
     _fields_ = [("latent_size", C.c_int32), ("num_linear", C.c_int32),
                 ("in_dim", C.c_int32 * MAX_LINEAR), ("out_dim", C.c_int32 * MAX_LINEAR),
-                ("latent_in_layer", C.c_int32)]
+                ("latent_in_layer", C.c_int32),
+                ("cat_kind", C.c_int32 * MAX_LINEAR), ("layer_norm", C.c_int32 * MAX_LINEAR),
+                ("use_tanh", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class Config(C.Structure):
@@ -68,6 +70,8 @@ SYMBOLS = [
     ("dspgn_last_error", C.c_char_p, []),
     ("dspgn_version", C.c_int, []),
     ("dspgn_decoder_create", C.c_int, [C.POINTER(DecoderSpec), C.POINTER(_FP), C.POINTER(_FP), C.c_int, C.POINTER(_VP)]),
+    ("dspgn_decoder_create_ex", C.c_int, [C.POINTER(DecoderSpec), C.POINTER(_FP), C.POINTER(_FP), C.POINTER(_FP), C.POINTER(_FP),
+                                          C.c_int, C.POINTER(_VP)]),
     ("dspgn_decoder_destroy", None, [_VP]),
     ("dspgn_solver_create", C.c_int, [C.POINTER(Config), C.POINTER(_VP), C.c_int, C.c_int, C.POINTER(_VP)]),
     ("dspgn_solver_destroy", None, [_VP]),

@@ -67,6 +67,7 @@ struct HostBuf {   // pinned staging
 
 struct DspgnDecoder {
   int device = 0;
+  bool has_ln = false;
   DspgnDecoderSpec spec{};
   DecoderDev dev{};
   std::vector<void*> allocs;
@@ -102,7 +103,7 @@ struct DspgnSolver {
   long long total_ray_tiles128 = 0;// ray-sample tiles of the batch
   int max_tiles128 = 0;            // largest tile count of one term of one object (queue items hold 19 bits)
   bool mega_enabled = true;
-  DevBuf d_clk, d_ev, d_seg;
+  DevBuf d_clk, d_ev, d_seg, d_ln;
   bool clk_on = false;
   HostBuf h_results;
   // counters
@@ -134,22 +135,31 @@ struct DspgnSolver {
 
 namespace {
 
+// what is concatenated at the input of layer k (latent_in_layer is shorthand for one kind-1 layer)
+int cat_kind_of(const DspgnDecoderSpec& s, int k) {
+  if (s.cat_kind[k] != 0) return s.cat_kind[k];
+  return (k == s.latent_in_layer) ? 1 : 0;
+}
+
 int check_spec(const DspgnDecoderSpec& s) {
   if (s.num_linear < 3 || s.num_linear > 9) return fail(DSPGN_E_ARG, "num_linear must be in [3,9]");
   if (s.latent_size < 1 || s.latent_size > DSPGN_MAX_CODE) return fail(DSPGN_E_ARG, "latent_size must be <= 64");
   const int in0 = s.latent_size + 3;
   if (s.in_dim[0] != in0) return fail(DSPGN_E_ARG, "in_dim[0] must equal latent_size+3");
   if (s.out_dim[s.num_linear - 1] != 1) return fail(DSPGN_E_ARG, "last layer must have one output");
+  if (s.latent_in_layer != -1 && (s.latent_in_layer < 1 || s.latent_in_layer > s.num_linear - 1))
+    return fail(DSPGN_E_ARG, "latent_in_layer must be a layer index >= 1 or -1");
   for (int k = 0; k < s.num_linear; ++k) {
     if (s.in_dim[k] < 1 || s.in_dim[k] > kHid || s.out_dim[k] < 1 || s.out_dim[k] > kHid)
       return fail(DSPGN_E_ARG, "layer widths must be in [1,256]");
+    const int ck = cat_kind_of(s, k);
+    if (ck < 0 || ck > 2 || (k == 0 && ck != 0)) return fail(DSPGN_E_ARG, "bad cat_kind");
+    if (s.layer_norm[k] != 0 && k == s.num_linear - 1) return fail(DSPGN_E_ARG, "the last layer cannot be normalised");
     if (k > 0) {
-      const int expect = s.out_dim[k - 1] + (k == s.latent_in_layer ? in0 : 0);
+      const int expect = s.out_dim[k - 1] + (ck == 1 ? in0 : (ck == 2 ? 3 : 0));
       if (s.in_dim[k] != expect) return fail(DSPGN_E_ARG, "layer in_dim inconsistent with previous out_dim/latent_in");
     }
   }
-  if (s.latent_in_layer != -1 && (s.latent_in_layer < 1 || s.latent_in_layer > s.num_linear - 2))
-    return fail(DSPGN_E_ARG, "latent_in_layer must be a hidden layer index or -1");
   return 0;
 }
 
@@ -171,7 +181,14 @@ int dspgn_version(void) { return 100; }
 
 int dspgn_decoder_create(const DspgnDecoderSpec* spec, const float* const* W, const float* const* b,
                          int device, DspgnDecoder** out) {
+  return dspgn_decoder_create_ex(spec, W, b, nullptr, nullptr, device, out);
+}
+
+int dspgn_decoder_create_ex(const DspgnDecoderSpec* spec, const float* const* W, const float* const* b,
+                            const float* const* ln_gamma, const float* const* ln_beta, int device, DspgnDecoder** out) {
   if (!spec || !W || !b || !out) return fail(DSPGN_E_ARG, "null argument");
+  for (int k = 0; k < spec->num_linear && k < DSPGN_MAX_LINEAR; ++k)
+    if (spec->layer_norm[k] && (!ln_gamma || !ln_beta || !ln_gamma[k] || !ln_beta[k])) return fail(DSPGN_E_ARG, "LayerNorm parameters missing");
   if (int rc = check_spec(*spec)) return rc;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(DSPGN_E_NOGPU, "no CUDA device"); }
@@ -185,8 +202,20 @@ int dspgn_decoder_create(const DspgnDecoderSpec* spec, const float* const* W, co
   d->device = device;
   d->spec = *spec;
   DecoderDev& dv = d->dev;
-  dv.L = spec->latent_size; dv.n_lin = spec->num_linear; dv.latent_in = spec->latent_in_layer; dv.in0 = spec->latent_size + 3;
+  dv.L = spec->latent_size; dv.n_lin = spec->num_linear; dv.in0 = spec->latent_size + 3;
   const int nl = spec->num_linear;
+  // variants: the plain shape (at most one latent_in layer among the hidden layers, nothing else) runs on both engines
+  int n_cat1 = 0, cat1_layer = -1;
+  bool generic = spec->use_tanh != 0;
+  for (int k = 0; k < nl; ++k) {
+    dv.cat_kind[k] = cat_kind_of(*spec, k);
+    if (dv.cat_kind[k] == 1) { ++n_cat1; cat1_layer = k; }
+    if (dv.cat_kind[k] == 2 || spec->layer_norm[k]) generic = true;
+  }
+  if (n_cat1 > 1 || (n_cat1 == 1 && cat1_layer > nl - 2)) generic = true;
+  dv.latent_in = (n_cat1 == 1) ? cat1_layer : -1;
+  dv.use_tanh = spec->use_tanh != 0; dv.generic = generic ? 1 : 0;
+  d->has_ln = false;
   int rc = 0;
   for (int k = 0; k < nl && rc == 0; ++k) {
     const int nin = spec->in_dim[k], nout = spec->out_dim[k];
@@ -209,8 +238,15 @@ int dspgn_decoder_create(const DspgnDecoderSpec* spec, const float* const* W, co
       for (int i = 0; i < nin; ++i) wl[i] = W[k][i];
       rc = upload_vec(d, wl, &dv.w_last);
     }
+    if (!rc && spec->layer_norm[k]) {
+      std::vector<float> g(kHid, 0.f), be(kHid, 0.f);
+      for (int j = 0; j < nout; ++j) { g[j] = ln_gamma[k][j]; be[j] = ln_beta[k][j]; }
+      rc = upload_vec(d, g, &dv.ln_gamma[k]);
+      if (!rc) rc = upload_vec(d, be, &dv.ln_beta[k]);
+      d->has_ln = true;
+    }
   }
-  if (!rc) rc = tc_pack_decoder(*spec, W, b, d->tc, &dv, g_err);
+  if (!rc && !generic) rc = tc_pack_decoder(*spec, W, b, d->tc, &dv, g_err);     // the tcgen05 engine covers the plain shape
   if (rc) { dspgn_decoder_destroy(d); return rc; }
   *out = d;
   return 0;
@@ -273,6 +309,11 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
   if (eng == DSPGN_ENGINE_TC && !tc_ok) { dspgn_solver_destroy(s); return fail(DSPGN_E_ARG, "tensor-core engine unavailable for this decoder shape"); }
   s->engine = eng;
   CU(cudaFuncSetAttribute(k_decoder_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimtSmem)));
+  for (auto* d : s->classes)
+    if (d->has_ln) {      // LayerNorm decoders: per-CTA scratch for the normalised activations (forward -> backward)
+      if (s->d_ln.reserve(4 * (size_t)s->num_sms * DSPGN_MAX_LINEAR * kHid * kTP)) { dspgn_solver_destroy(s); return fail(DSPGN_E_ALLOC, "cudaMalloc"); }
+      break;
+    }
   if (int rc = tc_setup_kernels(g_err)) { dspgn_solver_destroy(s); return rc; }
   if (const char* m = getenv("DSPGN_MEGA")) s->mega_enabled = (m[0] != '0');
   if (getenv("DSPGN_CLK")) {
@@ -305,7 +346,7 @@ void dspgn_solver_destroy(DspgnSolver* s) {
   dspgn_gather_close(s);
   for (DevBuf* b : {&s->d_decs, &s->d_stage, &s->d_state, &s->d_part_s, &s->d_part_r, &s->d_tbase, &s->d_V, &s->d_m, &s->d_results, &s->d_active,
                     &s->d_sdf, &s->d_bx, &s->d_bs, &s->d_br, &s->d_dbg, &s->d_clk, &s->d_q_items, &s->d_q_flag, &s->d_q_ctr,
-                    &s->d_tiles_left, &s->d_obj_iter, &s->d_ev, &s->d_seg}) b->release();
+                    &s->d_tiles_left, &s->d_obj_iter, &s->d_ev, &s->d_seg, &s->d_ln}) b->release();
   s->h_stage.release();
   s->h_results.release();
   for (auto e : s->ev) cudaEventDestroy(e);
@@ -511,6 +552,7 @@ TermArgs base_term(DspgnSolver* s, int mode) {
   a.part = (mode == MODE_BAND) ? s->d_part_r.as<float>() : (mode == MODE_SDF ? s->d_part_s.as<float>() : nullptr);
   a.tile_base = (mode == MODE_BAND) ? s->d_tbase.as<int>() + s->n_obj : (mode == MODE_SDF ? s->d_tbase.as<int>() : nullptr);
   a.D = s->cfg.num_depth_samples;
+  a.ln_scratch = s->d_ln.as<float>();
   a.dbg_J = nullptr; a.dbg_res = nullptr; a.dbg_obj = -1; a.dbg_P = 0;
   a.dbg_clk = (s->clk_on && mode == MODE_SDF) ? s->d_clk.as<long long>() : nullptr;
   return a;

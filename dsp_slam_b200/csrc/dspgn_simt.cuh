@@ -22,6 +22,11 @@ struct DecoderDev {
   const float* Wb[DSPGN_MAX_LINEAR];       // backward, reduction-major [out_pad16][256]: Wb[i*256+j] = W[i][j]
   const float* bias[DSPGN_MAX_LINEAR];     // [256] zero padded
   const float* w_last;                     // [256] last layer row
+  // optional variants (deep_sdf_decoder.py:41-47,58-63,87-102): SIMT engine only
+  int cat_kind[DSPGN_MAX_LINEAR];          // input of layer k = [activations | 0: nothing, 1: decoder input, 2: xyz]
+  const float* ln_gamma[DSPGN_MAX_LINEAR]; // LayerNorm after layer k (nullptr = none), [256] zero padded
+  const float* ln_beta[DSPGN_MAX_LINEAR];
+  int use_tanh, generic;                   // generic = any variant in use
   // tcgen05 engine images (dspgn_tc.cuh): pre-swizzled fp16 hi/lo weight chunks + step plan
   const unsigned char* tc_blob;
   TcPlan tc_plan;
@@ -53,6 +58,7 @@ struct TermArgs {
   float huber_b;
   // persistent kernel with the render term: the band rows' partials / tile bases / Huber threshold (SDF ones above)
   float* part_r; const int* tile_base_r; float huber_b1;
+  float* ln_scratch;         // SIMT engine, LayerNorm decoders: per-CTA [layer][256][kTP] normalised activations
   int D;
   int pose_only;             // 1: 6-D se3 Jacobian (no scale column)
   // debug dump of Jacobian rows (external order [pose | code]) for one object
@@ -195,7 +201,9 @@ __device__ __forceinline__ void gemm_rm(const float* __restrict__ Wg, int Kred, 
 
 struct SimtSmem {
   float act[kHid * kTP];             // feature-major activations / gradients / J rows
-  float inp[(kMaxCode + 4) * kTP];   // decoder input [z | x] rows, later the latent_in skip gradient
+  float inp[(kMaxCode + 4) * kTP];   // decoder input [z | x] rows
+  float gin[(kMaxCode + 4) * kTP];   // d sdf / d(input) collected from the concat layers (latent_in / xyz_in_all)
+  float lnst[DSPGN_MAX_LINEAR * kTP];       // LayerNorm: [layer][p] reciprocal std (the mean is not needed backward)
   float wbuf[2 * kKC * kHid];
   uint8_t mask[8 * kHid * 8];        // ReLU masks: [layer][feature][p/8] bit p%8
   float xo[3 * kTP];
@@ -204,6 +212,32 @@ struct SimtSmem {
   int prefix[kMaxObjScan + 1];
   int warp_tmp[32];
 };
+
+// LayerNorm backward (deep_sdf_decoder.py:96-102 through autograd): S.act holds the gradient w.r.t. the LN OUTPUT of
+// `layer` for its n features (already through the ReLU mask); turn it into the gradient w.r.t. the LN input:
+//   g_x = rstd * (gamma g - mean_j(gamma g) - xhat * mean_j(gamma g xhat)).     All threads; caller has synchronised.
+struct SimtSmem;
+__device__ inline void simt_ln_backward(float* act, float* red, const float* rstd, const float* __restrict__ gamma,
+                                        const float* __restrict__ xhat, int n) {
+  const int tid = threadIdx.x;
+  if (tid < kTP) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const float gg = act[j * kTP + tid] * gamma[j];
+      s1 += gg;
+      s2 = fmaf(gg, xhat[j * kTP + tid], s2);
+    }
+    red[tid] = s1 / (float)n;
+    red[kTP + tid] = s2 / (float)n;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * kTP; idx += kThreads) {
+    const int j = idx / kTP, p = idx - j * kTP;
+    const float gg = act[idx] * gamma[j];
+    act[idx] = rstd[p] * (gg - red[p] - xhat[idx] * red[kTP + p]);
+  }
+  __syncthreads();
+}
 
 __global__ void __launch_bounds__(kThreads, 1) k_decoder_simt(TermArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -245,6 +279,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_decoder_simt(TermArgs a) {
       S.rscale[p] = sc; S.rr[p] = res;
     }
     for (int idx = tid; idx < L * kTP; idx += kThreads) S.inp[idx] = st.z[idx / kTP];
+    for (int idx = tid; idx < (kMaxCode + 4) * kTP; idx += kThreads) S.gin[idx] = 0.f;
+    float* const xhat_all = (a.ln_scratch != nullptr) ? a.ln_scratch + (size_t)blockIdx.x * DSPGN_MAX_LINEAR * kHid * kTP : nullptr;
     __syncthreads();
     if (tid < 3 * kTP) S.inp[L * kTP + tid] = S.xo[tid];
     if (a.mode == MODE_RAYFWD) {
@@ -265,27 +301,82 @@ __global__ void __launch_bounds__(kThreads, 1) k_decoder_simt(TermArgs a) {
       gemm_rm(dec.Wf[k], dec.in_dim[k], (k == 0) ? S.inp : S.act, S.wbuf, acc);
       const int nout = dec.out_dim[k];
       const float* bias = dec.bias[k];
+      const float* lng = dec.ln_gamma[k];
+      if (lng == nullptr) {
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int j = 8 * jg + jj;
-        if (j < nout) {
-          const float bj = bias[j];
-          unsigned bits = 0;
-          float v[8];
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = 8 * jg + jj;
+          if (j < nout) {
+            const float bj = bias[j];
+            unsigned bits = 0;
+            float v[8];
 #pragma unroll
-          for (int pp = 0; pp < 8; ++pp) {
-            float t = acc[jj][pp] + bj;
-            bits |= (t > 0.f ? 1u : 0u) << pp;
-            v[pp] = fmaxf(t, 0.f);
+            for (int pp = 0; pp < 8; ++pp) {
+              float t = acc[jj][pp] + bj;
+              bits |= (t > 0.f ? 1u : 0u) << pp;
+              v[pp] = fmaxf(t, 0.f);
+            }
+            S.mask[(k * kHid + j) * 8 + pg] = (uint8_t)bits;
+            float4* dst = reinterpret_cast<float4*>(S.act + j * kTP + 8 * pg);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
           }
-          S.mask[(k * kHid + j) * 8 + pg] = (uint8_t)bits;
-          float4* dst = reinterpret_cast<float4*>(S.act + j * kTP + 8 * pg);
-          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      } else {
+        // ---- LayerNorm between the layer and its ReLU (deep_sdf_decoder.py:96-103), eps = 1e-5, biased variance ----
+        const float* lnb = dec.ln_beta[k];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = 8 * jg + jj;
+          if (j < nout) {
+            const float bj = bias[j];
+            float4* dst = reinterpret_cast<float4*>(S.act + j * kTP + 8 * pg);
+            dst[0] = make_float4(acc[jj][0] + bj, acc[jj][1] + bj, acc[jj][2] + bj, acc[jj][3] + bj);
+            dst[1] = make_float4(acc[jj][4] + bj, acc[jj][5] + bj, acc[jj][6] + bj, acc[jj][7] + bj);
+          }
+        }
+        __syncthreads();
+        if (tid < kTP) {
+          float m = 0.f;
+          for (int j = 0; j < nout; ++j) m += S.act[j * kTP + tid];
+          m /= (float)nout;
+          float var = 0.f;
+          for (int j = 0; j < nout; ++j) { const float d = S.act[j * kTP + tid] - m; var = fmaf(d, d, var); }
+          var /= (float)nout;
+          S.red[tid] = m;
+          S.lnst[k * kTP + tid] = 1.0f / sqrtf(var + 1e-5f);
+        }
+        __syncthreads();
+        float* xh_out = xhat_all + (size_t)k * kHid * kTP;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = 8 * jg + jj;
+          if (j < nout) {
+            const float gj = lng[j], bj = lnb[j];
+            unsigned bits = 0;
+            float v[8], xh[8];
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+              const int p = 8 * pg + pp;
+              xh[pp] = (S.act[j * kTP + p] - S.red[p]) * S.lnst[k * kTP + p];
+              const float t = fmaf(xh[pp], gj, bj);
+              bits |= (t > 0.f ? 1u : 0u) << pp;
+              v[pp] = fmaxf(t, 0.f);
+            }
+            S.mask[(k * kHid + j) * 8 + pg] = (uint8_t)bits;
+            float4* dst = reinterpret_cast<float4*>(S.act + j * kTP + 8 * pg);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            float4* xd = reinterpret_cast<float4*>(xh_out + j * kTP + 8 * pg);      // for the backward pass (L2-resident scratch)
+            xd[0] = make_float4(xh[0], xh[1], xh[2], xh[3]);
+            xd[1] = make_float4(xh[4], xh[5], xh[6], xh[7]);
+          }
         }
       }
-      if (k + 1 == dec.latent_in)      // deep_sdf_decoder.py:87-88: x = cat[x, input]
+      if (dec.cat_kind[k + 1] == 1)          // deep_sdf_decoder.py:87-88: x = cat[x, input]
         for (int idx = tid; idx < in0 * kTP; idx += kThreads) S.act[nout * kTP + idx] = S.inp[idx];
+      else if (dec.cat_kind[k + 1] == 2)     // deep_sdf_decoder.py:89-90: x = cat[x, xyz]
+        for (int idx = tid; idx < 3 * kTP; idx += kThreads) S.act[nout * kTP + idx] = S.inp[L * kTP + idx];
       __syncthreads();
     }
     {  // last layer (out = 1) + tanh
@@ -298,7 +389,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_decoder_simt(TermArgs a) {
       __syncthreads();
       if (tid < kTP) {
         float t = ((S.red[tid] + S.red[kTP + tid]) + S.red[2 * kTP + tid]) + S.red[3 * kTP + tid];
-        S.yv[tid] = tanhf(t + dec.bias[nl - 1][0]);
+        t += dec.bias[nl - 1][0];
+        float dfac = 1.f;
+        if (dec.use_tanh) { t = tanhf(t); dfac = 1.f - t * t; }        // deep_sdf_decoder.py:93-94
+        const float y = tanhf(t);                                       // :107-108
+        S.yv[tid] = y;
+        S.red[tid] = (1.f - y * y) * dfac;                              // d sdf / d(last layer output)
       }
       __syncthreads();
     }
@@ -318,18 +414,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_decoder_simt(TermArgs a) {
     // ---- phase 2: backward to the input ------------------------------------------------------
     {  // seed: g = (1 - y^2) W_last, masked by the last hidden ReLU
       const int kin = dec.in_dim[nl - 1];
+      const int ckl = dec.cat_kind[nl - 1];                                // the last layer's input may carry a concat too
+      const int ncl = kin - (ckl == 1 ? in0 : (ckl == 2 ? 3 : 0));
       for (int idx = tid; idx < kin * kTP; idx += kThreads) {
         const int j = idx / kTP, p = idx - j * kTP;
-        const float y = S.yv[p];
-        const unsigned bit = (S.mask[((nl - 2) * kHid + j) * 8 + (p >> 3)] >> (p & 7)) & 1u;
-        S.act[idx] = bit ? (1.f - y * y) * dec.w_last[j] : 0.f;
+        const float g = S.red[p] * dec.w_last[j];
+        if (j < ncl) {
+          const unsigned bit = (S.mask[((nl - 2) * kHid + j) * 8 + (p >> 3)] >> (p & 7)) & 1u;
+          S.act[idx] = bit ? g : 0.f;
+        } else {
+          S.gin[((ckl == 1 ? 0 : L) + (j - ncl)) * kTP + p] += g;
+        }
       }
       __syncthreads();
+      if (dec.ln_gamma[nl - 2] != nullptr)
+        simt_ln_backward(S.act, S.red + kTP, S.lnst + (nl - 2) * kTP, dec.ln_gamma[nl - 2], xhat_all + (size_t)(nl - 2) * kHid * kTP, ncl);
     }
     for (int k = nl - 2; k >= 0; --k) {
       gemm_rm(dec.Wb[k], dec.out_dim[k], S.act, S.wbuf, acc);
       const int nin = dec.in_dim[k];
-      const int ncont = (k == dec.latent_in) ? nin - in0 : nin;   // columns that continue down the chain
+      const int ck = dec.cat_kind[k];
+      const int ncont = (ck == 1) ? nin - in0 : (ck == 2 ? nin - 3 : nin);   // columns that continue down the chain
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const int j = 8 * jg + jj;
@@ -338,8 +443,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_decoder_simt(TermArgs a) {
 #pragma unroll
         for (int pp = 0; pp < 8; ++pp) v[pp] = acc[jj][pp];
         float* dst;
-        if (j >= ncont) {                       // latent_in skip path -> d/d(input), kept in S.inp
-          dst = S.inp + (j - ncont) * kTP + 8 * pg;
+        if (j >= ncont) {                       // concat path (latent_in: whole input, xyz_in_all: xyz) -> d/d(input)
+          dst = S.gin + ((ck == 1 ? 0 : L) + (j - ncont)) * kTP + 8 * pg;
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp) v[pp] += dst[pp];
         } else if (k > 0) {
           const unsigned bits = S.mask[((k - 1) * kHid + j) * 8 + pg];
 #pragma unroll
@@ -350,8 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decoder_simt(TermArgs a) {
           dst = S.act + jrow * kTP + 8 * pg;
 #pragma unroll
           for (int pp = 0; pp < 8; ++pp) {
-            float t = v[pp];
-            if (dec.latent_in >= 0) t += S.inp[j * kTP + 8 * pg + pp];
+            const float t = v[pp] + S.gin[j * kTP + 8 * pg + pp];
             v[pp] = t * S.rscale[8 * pg + pp];
           }
         }
@@ -359,6 +465,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_decoder_simt(TermArgs a) {
         reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
       }
       __syncthreads();
+      if (k > 0 && dec.ln_gamma[k - 1] != nullptr)      // through the LayerNorm of layer k-1 (its ReLU mask is applied above)
+        simt_ln_backward(S.act, S.red, S.lnst + (k - 1) * kTP, dec.ln_gamma[k - 1], xhat_all + (size_t)(k - 1) * kHid * kTP, ncont);
     }
     // ---- phase 3: Jacobian rows  J = [code (0..63) | pose (64..70) | 0] ---------------------------
     for (int idx = tid + L * kTP; idx < kMaxCode * kTP; idx += kThreads) S.act[idx] = 0.f;  // code_len < 64

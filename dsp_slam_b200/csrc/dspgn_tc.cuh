@@ -956,7 +956,7 @@ inline int tc_pack_decoder(const DspgnDecoderSpec& spec, const float* const* W, 
   h.ok = false;
   dv->tc_blob = nullptr;
   memset(&dv->tc_plan, 0, sizeof(TcPlan));
-  const int nl = spec.num_linear, in0 = spec.latent_size + 3, li = spec.latent_in_layer;
+  const int nl = spec.num_linear, in0 = spec.latent_size + 3, li = dv->latent_in;
   if (nl != 9 && nl < 3) return 0;
   if (in0 > 80) return 0;
   TcPlan& P = dv->tc_plan;

@@ -72,6 +72,18 @@ typedef struct {
   int32_t in_dim[DSPGN_MAX_LINEAR];
   int32_t out_dim[DSPGN_MAX_LINEAR];
   int32_t latent_in_layer;
+  /* Optional variants of deep_sdf_decoder.py (all zero = the plain decoder above):
+   *   cat_kind[k]   what is concatenated AFTER the activations at the input of layer k: 0 nothing, 1 the decoder
+   *                 input (latent_in, :87-88; several layers allowed), 2 xyz only (xyz_in_all, :89-90).
+   *                 latent_in_layer >= 0 is shorthand for cat_kind[latent_in_layer] = 1.
+   *   layer_norm[k] 1: LayerNorm (eps 1e-5) between layer k and its ReLU (:58-63,96-102); gamma/beta through
+   *                 dspgn_decoder_create_ex
+   *   use_tanh      1: an extra tanh on the last layer before the final one (:93-94,107-108)
+   * Decoders that use any of them run on the fp32 SIMT engine (the tcgen05 engine covers the plain shape). */
+  int32_t cat_kind[DSPGN_MAX_LINEAR];
+  int32_t layer_norm[DSPGN_MAX_LINEAR];
+  int32_t use_tanh;
+  int32_t reserved_;
 } DspgnDecoderSpec;
 
 /* The `optimizer` block of configs/config_*.json as read by reconstruct/optimizer.py:27-43. */
@@ -119,6 +131,10 @@ int dspgn_version(void);
 
 int dspgn_decoder_create(const DspgnDecoderSpec* spec, const float* const* W, const float* const* b,
                          int device, DspgnDecoder** out);
+/* the same with LayerNorm parameters: ln_gamma[k] / ln_beta[k] (out_dim[k] floats) for layers with layer_norm[k] = 1
+ * (entries of other layers are ignored; both arrays may be NULL when no layer is normalised) */
+int dspgn_decoder_create_ex(const DspgnDecoderSpec* spec, const float* const* W, const float* const* b,
+                            const float* const* ln_gamma, const float* const* ln_beta, int device, DspgnDecoder** out);
 void dspgn_decoder_destroy(DspgnDecoder* dec);
 
 int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, int n_classes,

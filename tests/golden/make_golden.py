@@ -305,9 +305,55 @@ def voxel_golden():
     print("voxel.npz written")
 
 
+def variant_golden():
+    """A decoder with every optional feature of deep_sdf_decoder.py switched on -- LayerNorm instead of weight-norm
+    (:58-63,96-102), xyz_in_all (:41-47,89-90), use_tanh (:93-94), TWO latent_in layers -- random weights (seeded),
+    run through the reference: forward, input Jacobian (loss_utils.get_batch_sdf_jacobian) and the SDF term."""
+    lu, lo = ns.loss_utils, ns.loss
+    spec = dict(latent_size=64, dims=[128, 160, 128, 192, 128], dropout=None, dropout_prob=0.0, norm_layers=[0, 1, 2, 3, 4],
+                latent_in=[2, 4], weight_norm=False, xyz_in_all=True, use_tanh=True, latent_dropout=False)
+    torch.manual_seed(11)
+    dec = ns.decoder.Decoder(**spec).eval()
+    with torch.no_grad():
+        for k in range(6):
+            lin = getattr(dec, f"lin{k}")
+            lin.weight.mul_(2.0)                      # keep activations alive through the ReLUs
+            if hasattr(dec, f"bn{k}"):
+                bn = getattr(dec, f"bn{k}")
+                bn.weight.copy_(1.0 + 0.3 * torch.randn_like(bn.weight))
+                bn.bias.copy_(0.2 * torch.randn_like(bn.bias))
+    sd = {k: v.detach().numpy().copy() for k, v in dec.state_dict().items()}
+    np.savez_compressed(os.path.join(HERE, "decoder_variant.npz"), spec_json=np.frombuffer(json.dumps(spec).encode(), dtype=np.uint8), **sd)
+    rng = np.random.default_rng(12)
+    obj = synth.make_object(13, 200, 0, 0)
+    t_oc = torch.inverse(torch.from_numpy(np.array(obj["t_cam_obj_init"])))
+    z = torch.from_numpy((0.3 * rng.standard_normal(64)).astype(np.float32))
+    pts = torch.from_numpy(np.ascontiguousarray(obj["pts"]))
+    x_obj = (pts[..., None, :] * t_oc[:3, :3]).sum(-1) + t_oc[:3, 3]
+    inp = torch.cat([z.expand(x_obj.shape[0], -1), x_obj], 1)
+    st = {}
+    with torch.no_grad():
+        st["dec_in"] = inp.numpy().copy()
+        st["dec_y"] = dec(inp).squeeze(-1).numpy().copy()
+    y, g = lu.get_batch_sdf_jacobian(dec, z, x_obj, 1)
+    st["jac_y"] = y.reshape(-1).numpy().copy()
+    st["jac_g"] = g.reshape(-1, 67).numpy().copy()
+    jt, jc, res = lo.compute_sdf_loss(dec, pts, t_oc, z)
+    st["sdf_t_cam_obj"] = np.array(obj["t_cam_obj_init"])
+    st["sdf_z"] = z.numpy().copy()
+    st["sdf_pts"] = pts.numpy().copy()
+    st["sdf_J"] = torch.cat([jt, jc], -1).reshape(-1, 71).numpy().copy()
+    st["sdf_res"] = res.reshape(-1).numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "variant.npz"), **st)
+    print("variant.npz written; sdf range", float(st["dec_y"].min()), float(st["dec_y"].max()))
+
+
 if __name__ == "__main__":
     if "--voxel-only" in sys.argv:
         voxel_golden()
+    elif "--variant-only" in sys.argv:
+        variant_golden()
     else:
         main()
         voxel_golden()
+        variant_golden()

@@ -637,3 +637,38 @@ def test_render_term_through_persistent_kernel(dec_path, cfg_kitti, oracle, orac
     for a_, b_ in zip(rs, rs3):
         if a_.is_good:
             np.testing.assert_array_equal(a_.t_cam_obj, b_.t_cam_obj)
+
+
+def test_decoder_variants_layernorm_xyz_in_all_use_tanh(golden_dir, cfg_kitti, oracle):
+    """Every optional feature of deep_sdf_decoder.py at once -- LayerNorm instead of weight-norm (:58-63,96-102),
+    xyz_in_all (:41-47,89-90), use_tanh (:93-94), two latent_in layers (:87-88) -- through the fp32 SIMT engine
+    (selected automatically; the tcgen05 engine covers the plain shape and refuses this one loudly) against the
+    REFERENCE's own forward values, input Jacobian and SDF-term rows (tests/golden/variant.npz)."""
+    from dsp_slam_b200.optimizer import Optimizer
+    from dsp_slam_b200.decoder import DecoderWeights
+    from dsp_slam_b200._lib import DspgnError, ENGINE_SIMT
+    path = os.path.join(golden_dir, "decoder_variant.npz")
+    st = np.load(os.path.join(golden_dir, "variant.npz"))
+    w = DecoderWeights.from_npz(path)
+    assert not w.is_plain and w.cat_kind == [0, 2, 1, 2, 1, 2] and w.use_tanh
+    opt = Optimizer(path, cfg_kitti, sdf_only=True)                     # engine auto -> SIMT
+    assert opt.solver.engine == ENGINE_SIMT
+    with pytest.raises(DspgnError):
+        Optimizer(path, cfg_kitti, sdf_only=True, engine="tc")
+    # forward (decode_sdf) vs the reference
+    s = opt.solver.decode_sdf(st["sdf_z"], st["dec_in"][:, 64:67])
+    np.testing.assert_allclose(s, st["dec_y"], rtol=0, atol=3e-6)
+    # SDF term: residuals and Jacobian rows [pose | code] vs loss.compute_sdf_loss
+    n = st["sdf_pts"].shape[0]
+    opt.solver.upload([dict(t_cam_obj=st["sdf_t_cam_obj"], pts=st["sdf_pts"], code=st["sdf_z"])])
+    g = opt.solver.debug_system(0, 0, want_rows=True, n_pts=n)
+    np.testing.assert_allclose(g["res"], st["sdf_res"], rtol=0, atol=3e-6)
+    assert rel(g["J"], st["sdf_J"]) < 3e-5
+    # the assembled system vs the oracle (which is itself pinned to the same golden on CPU)
+    odw = oracle.DecoderWeights.from_npz(path)
+    it = oracle.gn_iteration(odw, oracle.GNConfig.from_json_dict(cfg_kitti), oracle.inv4(st["sdf_t_cam_obj"]), st["sdf_z"],
+                             st["sdf_pts"], None, None, sdf_only=True)
+    assert rel(g["H"], it["H"]) < 1e-4 and rel(g["b"], it["b"]) < 1e-4
+    # and a whole run converges to a finite result
+    r = opt.reconstruct_batch([dict(t_cam_obj=st["sdf_t_cam_obj"], pts=st["sdf_pts"], code=st["sdf_z"])])[0]
+    assert r.is_good and np.isfinite(r.t_cam_obj).all()

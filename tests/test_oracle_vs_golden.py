@@ -129,6 +129,39 @@ def test_whole_runs(oracle, oracle_decoders, cfg_kitti, cfg_redwood, golden_dir,
     assert abs(float(out["loss"]) - float(d["loss"])) < 0.05 * abs(float(d["loss"])) + 1e-5
 
 
+def test_full_size_and_batched_goldens(oracle, oracle_decoders, cfg_kitti, cfg_redwood, golden_dir):
+    """The oracle against the reference at FULL size (config 2 with the render term: 2048 pts + 2248 rays, V ~ 1e5, band
+    rows in the thousands) and on config 3's batch of 8: the render counters V and m of every iteration until the
+    trajectories separate, iteration 0 tightly, the end state to the measured noise floor."""
+    d = np.load(os.path.join(golden_dir, "recon_cfg2full.npz"))
+    cfg = oracle.GNConfig.from_json_dict(cfg_kitti)
+    tr = []
+    out = oracle.reconstruct_object(oracle_decoders["cars"], cfg, d["in_t_cam_obj"], d["in_pts"], d["in_rays"], d["in_depth"], trace=tr)
+    assert out["is_good"]
+    # 112,400 samples: one |x| < 1 boundary decision flips between two fp32 evaluations of x_o (not a band sample)
+    assert abs(tr[0]["V"] - int(d["V_iters"][0])) <= 2 and tr[0]["m"] == int(d["m_iters"][0])
+    # fp32 summation over 3814 + 2048 rows in a different order than torch.bmm().sum(0): 7e-5
+    assert rel(tr[0]["H"], d["H_iters"][0]) < 2e-4 and rel(tr[0]["b"], d["b_iters"][0]) < 2e-4
+    for k in range(10):                                     # thousands of band rows: single flips only
+        assert abs(tr[k]["V"] - int(d["V_iters"][k])) <= 20 and abs(tr[k]["m"] - int(d["m_iters"][k])) <= 0.01 * d["m_iters"][k] + 3
+    assert np.abs(out["t_cam_obj"] - d["t_cam_obj"]).max() < 5e-3 and np.abs(out["code"] - d["code"]).max() < 2e-3   # SURVEY B.3
+    d = np.load(os.path.join(golden_dir, "recon_cfg3_b8.npz"))
+    cfg = oracle.GNConfig.from_json_dict(cfg_redwood)
+    cfg.num_iterations = 10
+    errs = []
+    for i in range(8):
+        tr = []
+        out = oracle.reconstruct_object(oracle_decoders["chairs"], cfg, d["in_t_cam_obj"][i], d["in_pts"][i], d["in_rays"][i],
+                                        d["in_depth"][i], code=d["in_code"][i], trace=tr)
+        assert out["is_good"] and bool(d["is_good"][i])
+        assert tr[0]["V"] == int(d["V_iters"][i, 0]) and tr[0]["m"] == int(d["m_iters"][i, 0])
+        assert rel(tr[0]["H"], d["H_iters"][i, 0]) < 5e-5 and np.abs(tr[0]["dx"] - d["dx_iters"][i, 0]).max() < 1e-4
+        assert rel(tr[1]["H"], d["H_iters"][i, 1]) < 2e-2 and tr[1]["V"] == int(d["V_iters"][i, 1])
+        errs.append(float(np.abs(out["t_cam_obj"] - d["t_cam_obj"][i]).max()))
+    # ~100 band rows per object: chaotic; 7 of 8 objects stay within 3e-2 of the reference, one separates (0.59)
+    assert sorted(errs)[6] < 3e-2 and np.median(errs) < 1e-2, errs
+
+
 def test_soft_failure_too_few_samples(oracle, oracle_decoders, cfg_kitti, golden_dir):
     d = np.load(os.path.join(golden_dir, "recon_fail_few.npz"))
     assert not bool(d["is_good"])
@@ -149,3 +182,17 @@ def test_decode_sdf_on_reference_voxel_grid(oracle, oracle_decoders, golden_dir)
     v = np.load(os.path.join(golden_dir, "voxel.npz"))
     s = oracle.decode_sdf(oracle_decoders["cars"], v["z"], v["vox8"])
     np.testing.assert_allclose(s, v["vox8_sdf"], rtol=0, atol=2e-7)
+
+
+def test_decoder_variants_vs_reference(oracle, golden_dir):
+    """LayerNorm + xyz_in_all + use_tanh + two latent_in layers (deep_sdf_decoder.py:41-47,58-63,87-102): the oracle's
+    forward, input Jacobian and SDF-term rows against the reference's (tests/golden/variant.npz)."""
+    dw = oracle.DecoderWeights.from_npz(os.path.join(golden_dir, "decoder_variant.npz"))
+    st = np.load(os.path.join(golden_dir, "variant.npz"))
+    assert dw.xyz_in_all and dw.use_tanh and dw.latent_in == (2, 4) and sum(x is not None for x in dw.ln) == 5
+    y, g = oracle.decoder_value_and_input_grad(dw, st["dec_in"])
+    np.testing.assert_allclose(y, st["dec_y"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(y, st["jac_y"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(g, st["jac_g"], rtol=0, atol=5e-6)
+    J, res = oracle.sdf_term(dw, st["sdf_pts"], oracle.inv4(st["sdf_t_cam_obj"]), st["sdf_z"])
+    assert rel(J, st["sdf_J"]) < 1e-5 and np.abs(res - st["sdf_res"]).max() < 3e-6
