@@ -682,7 +682,7 @@ int run_batch_impl(DspgnSolver* s, int mode) {
     bad |= s->d_q_flag.reserve(4 * (size_t)cap);
     bad |= s->d_q_ctr.reserve(4 * 128);
     bad |= s->d_tiles_left.reserve(4 * 3 * (size_t)s->n_obj);
-    const size_t nseg_cap = (size_t)s->tot_rays / kSegRays + s->n_obj + 2;
+    const size_t nseg_cap = (size_t)s->tot_rays / kSegRays + 2 * (size_t)s->n_obj + 4;
     if (render) bad |= s->d_seg.reserve(4 * 2 * nseg_cap);
     bad |= s->d_obj_iter.reserve(4 * (size_t)s->n_obj);
     if (bad) return fail(DSPGN_E_ALLOC, "queue allocation failed");

@@ -423,14 +423,10 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
     int bad_pivot = 0;
 #pragma unroll 1
     for (int k = 0; k < kPMax; ++k) {
-      // after k rotations only entries 0 .. 71-k of a rotated row can be non-zero: the (warp-uniform) tail of every
-      // broadcast / load / update loop is skipped, which halves the shared-memory traffic and the FMA chain on average
-      const int live = kPMax + 1 - k;                              // entries [0, live) matter (entry `live-1` is the zero pad at k = 0)
       float4* buf = bcast[k & 1];
       if (tid == k) {
 #pragma unroll
-        for (int j = 0; j <= kPMax; j += 4)
-          if (j < live) buf[j >> 2] = make_float4(arow[j], arow[j + 1], arow[j + 2], arow[j + 3]);
+        for (int j = 0; j <= kPMax; j += 4) buf[j >> 2] = make_float4(arow[j], arow[j + 1], arow[j + 2], arow[j + 3]);
         buf[(kPMax + 1) / 4] = make_float4(brow, 0.f, 0.f, 0.f);
         mydiag = arow[0];
       }
@@ -438,28 +434,15 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
       float pr[kPMax + 1];
 #pragma unroll
       for (int j = 0; j <= kPMax; j += 4) {
-        if (j < live) {
-          const float4 v = buf[j >> 2];
-          pr[j] = v.x; pr[j + 1] = v.y; pr[j + 2] = v.z; pr[j + 3] = v.w;
-        } else {
-          pr[j] = 0.f; pr[j + 1] = 0.f; pr[j + 2] = 0.f; pr[j + 3] = 0.f;
-        }
+        const float4 v = buf[j >> 2];
+        pr[j] = v.x; pr[j + 1] = v.y; pr[j + 2] = v.z; pr[j + 3] = v.w;
       }
       const float pb = buf[(kPMax + 1) / 4].x;
       const float piv = pr[0];
       if (!(piv > 0.f) || !(piv < 3.0e38f)) bad_pivot = 1;        // every thread sees the same pivot
       const float l = (tid == k) ? 0.f : arow[0] * __frcp_rn(piv);
 #pragma unroll
-      for (int j = 0; j <= kPMax; j += 4) {
-        if (j < live) {
-          if (j > 0) arow[j - 1] = fmaf(-l, pr[j], arow[j]);
-          arow[j] = fmaf(-l, pr[j + 1], arow[j + 1]);
-          arow[j + 1] = fmaf(-l, pr[j + 2], arow[j + 2]);
-          if (j + 3 <= kPMax) arow[j + 2] = fmaf(-l, pr[j + 3], arow[j + 3]);
-        } else if (j > 0 && j - 4 < live) {
-          arow[j - 1] = 0.f;                                       // the entry that rotates in behind the live range
-        }
-      }
+      for (int j = 1; j <= kPMax; ++j) arow[j - 1] = fmaf(-l, pr[j], arow[j]);
       brow = fmaf(-l, pb, brow);
     }
     if (tid < kPMax) xs[tid] = brow / mydiag;
@@ -634,7 +617,8 @@ __device__ __forceinline__ int ray_emit(const ScanArgs& a, const ObjMeta& M, con
 // sample range (single pass, all sdf loads of the segment issued up front).  Band rows keep the global (ray, sample)
 // order; band tiles find them through the per-object exclusive prefix over the segment counts.
 constexpr int kSegRays = 8, kScanChunkRays = 64;
-__device__ __forceinline__ int seg_base(const ObjMeta& M, int o) { return M.ray_off / kSegRays + o; }   // first segment slot of object o
+// first segment slot of object o: its nseg counts / nseg + 1 prefix entries never overlap the next object's
+__device__ __forceinline__ int seg_base(const ObjMeta& M, int o) { return M.ray_off / kSegRays + 2 * o; }
 
 __device__ inline void scan_chunk(const ScanArgs& a, int* seg_cnt, const int o, const int chunk, const int tid) {
   const int lane = tid & 31, warp = tid >> 5;

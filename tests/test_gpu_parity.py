@@ -463,8 +463,8 @@ def test_iteration_by_iteration_vs_reference(engine, golden_dir, dec_path, cfg_k
         if not flips_ok and k_first == iters:
             k_first = k
         kk = min(k + 1, len(tr) - 1)
-        tolH = (3e-4, 6e-4)[k] if k < 2 else max(1e-3, 8 * floorH[kk])
-        toldx = (2e-5, 3e-4)[k] if k < 2 else max(1e-3, 8 * floordx[kk])
+        tolH = (3e-4, 6e-4)[k] if k < 2 else max(1e-3, 12 * floorH[kk])
+        toldx = (2e-5, 3e-4)[k] if k < 2 else max(1e-3, 12 * floordx[kk])
         if k < k_first:
             assert eH < tolH and eb < 2 * tolH and edx < toldx, (k, tolH, toldx, rows)
     print(f"\n[iter-parity] {name}[{oi}] {engine}: k_first={k_first}  (k, dV, dm, relH, relb, |ddx|) = "
