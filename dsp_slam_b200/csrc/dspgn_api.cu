@@ -118,6 +118,7 @@ struct DspgnSolver {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_upload = nullptr;   // the pinned staging block may be rewritten only after its last H2D copy finished
   bool upload_pending = false;
+  bool mega_ran = false;             // the last run used the persistent kernel: check its abort flag with the results
   bool band_rows_pending = false;    // the persistent kernel's band-row total has not been added to ctr yet
   int n_bad = 0;                     // resident objects rejected at upload (status BAD_INPUT, never evaluated)
   // multi-GPU result exchange (rank 0 owns the buffer, the others map it through CUDA IPC)
@@ -571,7 +572,7 @@ int launch_init(DspgnSolver* s, int pose_only, bool mega = false, bool render = 
     ia.q0_off = render ? s->d_q0_render : s->d_tbase_static; ia.tile_rows = kTcRows;
     ia.q_items = s->d_q_items.as<int>(); ia.q_flag = s->d_q_flag.as<int>();
     ia.q_head = s->d_q_ctr.as<int>(); ia.q_tail = s->d_q_ctr.as<int>() + 32; ia.done_objects = s->d_q_ctr.as<int>() + 64;
-    ia.band_rows_total = s->d_q_ctr.as<int>() + 80;
+    ia.band_rows_total = s->d_q_ctr.as<int>() + 80; ia.abort_flag = s->d_q_ctr.as<int>() + 96;
     ia.pending = s->d_tiles_left.as<int>(); ia.ray_left = s->d_tiles_left.as<int>() + s->n_obj;
     ia.obj_iter = s->d_obj_iter.as<int>();
     ia.total_tiles0 = s->total_tiles128 + (render ? (int)s->total_ray_tiles128 : 0);
@@ -701,6 +702,7 @@ int run_batch_impl(DspgnSolver* s, int mode) {
     q.q_items = s->d_q_items.as<int>(); q.q_flag = s->d_q_flag.as<int>();
     q.q_head = s->d_q_ctr.as<int>(); q.q_tail = s->d_q_ctr.as<int>() + 32; q.done_objects = s->d_q_ctr.as<int>() + 64;
     q.band_rows_total = s->d_q_ctr.as<int>() + 80;
+    q.abort_flag = s->d_q_ctr.as<int>() + 96;
     q.pending = s->d_tiles_left.as<int>(); q.ray_left = s->d_tiles_left.as<int>() + s->n_obj; q.obj_iter = s->d_obj_iter.as<int>();
     q.scan_left = s->d_tiles_left.as<int>() + 2 * s->n_obj;
     q.seg_cnt = s->d_seg.as<int>(); q.seg_prefix = s->d_seg.as<int>() + nseg_cap;
@@ -719,6 +721,7 @@ int run_batch_impl(DspgnSolver* s, int mode) {
     s->ctr.rows_fwd_bwd += (long long)s->tot_pts * iters;
     if (render) s->ctr.rows_fwd_only += s->tot_smp * iters;
     s->band_rows_pending = render;
+    s->mega_ran = true;
     CU(cudaGetLastError());
     CU(cudaEventRecord(s->ev_run1, s->stream));
     return 0;
@@ -919,6 +922,12 @@ int dspgn_results(DspgnSolver* s, DspgnObjectOut* out) {
   CU(cudaMemcpyAsync(s->h_results.p, s->d_results.p, bytes, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   memcpy(out, s->h_results.p, bytes);
+  if (s->mega_ran) {
+    int aborted = 0;
+    if (cudaMemcpy(&aborted, s->d_q_ctr.as<int>() + 96, 4, cudaMemcpyDeviceToHost) != cudaSuccess) cudaGetLastError();
+    s->mega_ran = false;
+    if (aborted) return fail(DSPGN_E_CUDA, "persistent kernel: a work-queue wait timed out (aborted softly; results incomplete)");
+  }
   if (s->band_rows_pending) {          // band rows the persistent kernel processed (data dependent): roofline accounting
     int m_total = 0;
     if (cudaMemcpy(&m_total, s->d_q_ctr.as<int>() + 80, 4, cudaMemcpyDeviceToHost) == cudaSuccess) s->ctr.rows_fwd_bwd += m_total;

@@ -87,6 +87,7 @@ struct MegaArgs {
   int* obj_iter;             // [n_obj] current iteration of each object
   int* done_objects;         // objects finished (last iteration or frozen)
   int* band_rows_total;      // sum of band rows over all objects and iterations (roofline accounting)
+  int* abort_flag;           // set when a queue wait timed out: every CTA drains and exits (soft failure, never a trap)
   long long* ev; int ev_cap; // optional event log (env DSPGN_CLK): ev[0] = count, then {globaltimer ns, kind<<48|sm<<32|o<<20|tile}
 };
 // event kinds of the persistent kernel's debug log

@@ -120,7 +120,7 @@ struct InitArgs {
   int n_obj, code_len, D, pose_only;
   // persistent-kernel mode: also seed the work queue with every object's iteration-0 tiles (ray-sample tiles first)
   int mega; int render; const int* q0_off; int tile_rows; int* q_items; int* q_flag; int* q_head; int* q_tail;
-  int* pending; int* ray_left; int* obj_iter; int* done_objects; int* band_rows_total; int total_tiles0;
+  int* pending; int* ray_left; int* obj_iter; int* done_objects; int* band_rows_total; int* abort_flag; int total_tiles0;
   GatherDev gather;
   float* results;          // records of objects rejected at upload are written here
   int n_bad;
@@ -158,7 +158,7 @@ __global__ void k_init(InitArgs a) {
     for (int j = tid; j < ntF; j += blockDim.x) { a.q_items[base + j] = make_item(MODE_RAYFWD, o, j); a.q_flag[base + j] = 1; }
     for (int j = tid; j < ntS; j += blockDim.x) { a.q_items[base + ntF + j] = make_item(MODE_SDF, o, j); a.q_flag[base + ntF + j] = 1; }
     if (tid == 0) { a.pending[o] = ntS + (ntF > 0 ? 1 : 0); a.ray_left[o] = ntF; a.obj_iter[o] = 0; }
-    if (o == 0 && tid == 0) { *a.q_head = 0; *a.q_tail = a.total_tiles0; *a.done_objects = a.n_bad; *a.band_rows_total = 0; }
+    if (o == 0 && tid == 0) { *a.q_head = 0; *a.q_tail = a.total_tiles0; *a.done_objects = a.n_bad; *a.band_rows_total = 0; *a.abort_flag = 0; }
   }
 }
 

@@ -235,14 +235,23 @@ __device__ __forceinline__ void unit_done(uint64_t* bar) {
 struct TileRef { int o, row0, slot, mode, tile; };
 
 // pop one work item for this CTA (persistent mode); -1 = no more work anywhere
+// A wait that outlives kMegaTimeoutNs (wall clock, so it also holds under compute-sanitizer / a debugger) raises the
+// abort flag: every CTA drains and exits, the host reports DSPGN_E_CUDA.  No __trap: a trap would poison the CUDA
+// context of the whole process (the detectors on the Tracking thread live in it too).
+constexpr unsigned long long kMegaTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;
 __device__ inline int mega_pop(const MegaArgs& q, int n_obj) {
   const int t = atomicAdd(q.q_head, 1);
   if (t >= q.q_cap) return -1;
+  unsigned long long t0 = 0;
   for (unsigned spins = 0;; ++spins) {
     if (ldv(q.q_flag + t) != 0) { __threadfence(); return ldv(q.q_items + t); }
-    if (ldv(q.done_objects) >= n_obj) return -1;
+    if (ldv(q.done_objects) >= n_obj || ldv(q.abort_flag) != 0) return -1;
     __nanosleep(256);
-    if (spins > (1u << 24)) __trap();              // ~seconds: never hang the GPU on a logic error
+    if ((spins & 1023u) == 1023u) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kMegaTimeoutNs) { atomicExch(q.abort_flag, 1); return -1; }
+    }
   }
 }
 
@@ -260,7 +269,7 @@ __device__ __forceinline__ bool tile_at(const TermArgs& a, TcSmemTail& S, int se
     return true;
   } else {
     volatile int* pub = &S.fifo_pub;
-    for (unsigned spins = 0; *pub <= seq; ++spins) { __nanosleep(64); if (spins > (1u << 26)) __trap(); }
+    while (*pub <= seq) __nanosleep(64);           // filled by this CTA's scheduler lane, which always terminates (mega_pop)
     const int item = reinterpret_cast<volatile int*>(S.fifo)[seq & 3];
     if (item < 0) return false;
     t.o = (item >> kItemObjShift) & kItemObjMask;
@@ -355,7 +364,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         if (MEGA) {
           // scheduler: fetch this CTA's next tile into the local FIFO (at most 3 entries ahead of the epilogue)
           volatile int* es = &S.epi_seq;
-          for (unsigned spins = 0; seq - *es >= 3; ++spins) { __nanosleep(64); if (spins > (1u << 26)) __trap(); }
+          while (seq - *es >= 3) __nanosleep(64);   // the epilogue warps always make progress (bounded tile work)
           const int item = mega_pop(q, a.n_obj);
           if (item >= 0) mega_event(q, EV_POPPED, item >> kItemKindShift, (item >> kItemObjShift) & kItemObjMask, item & kItemTileMask);
           reinterpret_cast<volatile int*>(S.fifo)[seq & 3] = item;
