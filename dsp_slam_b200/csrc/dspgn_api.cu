@@ -715,7 +715,8 @@ int run_batch_impl(DspgnSolver* s, int mode) {
     v.base_s = s->d_tbase_static; v.base_r = s->d_tbase_r_static; v.tile_rows = kTcRows; v.last_iter = 0; v.iter_index = 0; v.dbg_clk = nullptr;
     ScanArgs sa = base_scan(s);
     if (s->timing) cudaEventRecord(next_event(s), s->stream);
-    k_gn_persistent<<<s->num_sms, kTcThreads, kTcSmemBytes, s->stream>>>(a, q, v, sa);
+    if (render) k_gn_persistent_render<<<s->num_sms, kTcThreads, kTcSmemBytes, s->stream>>>(a, q, v, sa);
+    else k_gn_persistent<<<s->num_sms, kTcThreads, kTcSmemBytes, s->stream>>>(a, q, v);
     if (s->timing) cudaEventRecord(next_event(s), s->stream);
     s->ctr.kernel_launches += 1;
     s->ctr.rows_fwd_bwd += (long long)s->tot_pts * iters;

@@ -440,7 +440,7 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
       const float pb = buf[(kPMax + 1) / 4].x;
       const float piv = pr[0];
       if (!(piv > 0.f) || !(piv < 3.0e38f)) bad_pivot = 1;        // every thread sees the same pivot
-      const float l = (tid == k) ? 0.f : arow[0] * __frcp_rn(piv);
+      const float l = (tid == k) ? 0.f : __fdividef(arow[0], piv);        // MUFU.RCP path: 47 vs 112 cycles per pivot for __frcp_rn (tools/probes/solve_probe.cu)
 #pragma unroll
       for (int j = 1; j <= kPMax; ++j) arow[j - 1] = fmaf(-l, pr[j], arow[j]);
       brow = fmaf(-l, pb, brow);

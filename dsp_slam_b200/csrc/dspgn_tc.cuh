@@ -256,8 +256,11 @@ __device__ inline int mega_pop(const MegaArgs& q, int n_obj) {
 }
 
 // tile number `seq` of this CTA: static round-robin over the launch's tiles, or the CTA-local FIFO
-template <bool MEGA>
+// SCHED: 0 = one launch per term (static tiles), 1 = persistent kernel, SDF tiles only (SDF-only joint runs, pose-only
+// runs: the tile kind is a compile-time constant), 2 = persistent kernel with the render term (all item kinds)
+template <int SCHED>
 __device__ __forceinline__ bool tile_at(const TermArgs& a, TcSmemTail& S, int seq, int total_tiles, TileRef& t) {
+  constexpr bool MEGA = SCHED != 0;
   if (!MEGA) {
     const int tile = blockIdx.x + seq * gridDim.x;
     if (tile >= total_tiles) return false;
@@ -273,7 +276,7 @@ __device__ __forceinline__ bool tile_at(const TermArgs& a, TcSmemTail& S, int se
     const int item = reinterpret_cast<volatile int*>(S.fifo)[seq & 3];
     if (item < 0) return false;
     t.o = (item >> kItemObjShift) & kItemObjMask;
-    t.mode = item >> kItemKindShift;
+    t.mode = (SCHED == 1) ? MODE_SDF : (item >> kItemKindShift);
     const int j = item & kItemTileMask;
     t.tile = j;
     t.row0 = j * kTcRows;
@@ -327,8 +330,10 @@ __device__ __noinline__ void mega_solve_and_advance(const TermArgs& a, const Meg
   }
 }
 
-template <bool MEGA>
+template <int SCHED>
 __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, const SolveArgs& sv, const ScanArgs& sc_args) {
+  constexpr bool MEGA = SCHED != 0;
+  constexpr bool RENDER = SCHED == 2;
   extern __shared__ unsigned char tc_smem_raw[];
   unsigned char* ring = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   TcSmemTail& S = *reinterpret_cast<TcSmemTail*>(ring + (size_t)kTcStages * kTcStageBytes);
@@ -372,13 +377,13 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
           *reinterpret_cast<volatile int*>(&S.fifo_pub) = seq + 1;
         }
         TileRef tr;
-        if (!tile_at<MEGA>(a, S, seq, total_tiles, tr)) break;
+        if (!tile_at<SCHED>(a, S, seq, total_tiles, tr)) break;
         const int o = tr.o;
         const int cls = a.meta[o].class_id;
         const TcPlan& plan = S.plans[cls];
         const unsigned char* blob = a.decs[cls].tc_blob;
         const bool fwd_only = (tr.mode == MODE_RAYFWD || tr.mode == MODE_PTSFWD);
-        const int ns = (MEGA && tr.mode == kKindScan) ? 0 : (fwd_only ? plan.n_fwd : plan.n_steps);
+        const int ns = (RENDER && tr.mode == kKindScan) ? 0 : (fwd_only ? plan.n_fwd : plan.n_steps);
         for (int s = 0; s < ns; ++s) {
           const TcStep st = plan.step[s];
           const uint32_t img = (uint32_t)st.n_mma * 128u;
@@ -403,11 +408,11 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
     for (int seq = 0;; ++seq) {
       ++clk_tile;
       TileRef tr;
-      if (!tile_at<MEGA>(a, S, seq, total_tiles, tr)) break;
+      if (!tile_at<SCHED>(a, S, seq, total_tiles, tr)) break;
       const int o = tr.o;
       const TcPlan& plan = S.plans[a.meta[o].class_id];
       const bool fwd_only = (tr.mode == MODE_RAYFWD || tr.mode == MODE_PTSFWD);
-      const int ns = (MEGA && tr.mode == kKindScan) ? 0 : (fwd_only ? plan.n_fwd : plan.n_steps);
+      const int ns = (RENDER && tr.mode == kKindScan) ? 0 : (fwd_only ? plan.n_fwd : plan.n_steps);
       for (int s = 0; s < ns; ++s) {
         const TcStep st = plan.step[s];
         const uint32_t d_t = tmem + (uint32_t)st.d_reg * 256u;
@@ -472,9 +477,9 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
     for (int seq = 0;; ++seq) {
       ++clk_tile;
       TileRef tr;
-      if (!tile_at<MEGA>(a, S, seq, total_tiles, tr)) break;
+      if (!tile_at<SCHED>(a, S, seq, total_tiles, tr)) break;
       if (MEGA && tid == 0) { *reinterpret_cast<volatile int*>(&S.epi_seq) = seq + 1; mega_event(q, EV_TILE_BEGIN, tr.mode, tr.o, tr.tile); }
-      if (MEGA && tr.mode == kKindScan) {
+      if (RENDER && tr.mode == kKindScan) {
         // ---- scan item: occupancy scan / rendered depth / band rows of 64 rays (loss.py:84-141); no GEMM steps ----------
         const int o = tr.o;
         scan_chunk(sc_args, q.seg_cnt, o, tr.tile, tid);
@@ -517,8 +522,8 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
       const bool fwd_only = (mode == MODE_RAYFWD || mode == MODE_PTSFWD);
       const int nrows = min(kTcRows, (MEGA ? mega_rows(a, M, o, mode) : term_rows(a, o)) - row0);
       const int ns = fwd_only ? plan.n_fwd : plan.n_steps;
-      const float huber_b = (MEGA && mode == MODE_BAND) ? a.huber_b1 : a.huber_b;
-      float* const part = (MEGA && mode == MODE_BAND) ? a.part_r : a.part;
+      const float huber_b = (RENDER && mode == MODE_BAND) ? a.huber_b1 : a.huber_b;
+      float* const part = (RENDER && mode == MODE_BAND) ? a.part_r : a.part;
       // the pose / code of this object may have been rewritten by another CTA's solve: bypass L1
       float Toc[12];
 #pragma unroll
@@ -540,7 +545,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
       }
       const int* segp = nullptr;
       int nseg = 0;
-      if (MEGA && mode == MODE_BAND) {
+      if (RENDER && mode == MODE_BAND) {
         // band rows live compacted per 8-ray segment: stage the object's segment prefix (<= 1025 ints) in the idle J tile
         nseg = (M.n_rays + kSegRays - 1) / kSegRays;
         int* sp = reinterpret_cast<int*>(S.Jp);
@@ -559,7 +564,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         } else if (mode == MODE_BAND) {
           // band rows were written by the CTAs that ran this object's scan: L2 is the point of coherence
           size_t sidx = (size_t)M.smp_off + rr_;
-          if (MEGA) {
+          if (RENDER) {
             int lo = 0, hi = nseg;                     // largest segment with prefix <= row
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (segp[mid] <= rr_) lo = mid; else hi = mid; }
             sidx = (size_t)M.smp_off + (size_t)lo * kSegRays * a.D + (size_t)(rr_ - segp[lo]);
@@ -820,13 +825,13 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         if (tid == 0) {
           mega_event(q, EV_TILE_END, mode, o, tr.tile);
           int act = 0;
-          if (mode == MODE_RAYFWD) { if (atomicSub(q.ray_left + o, 1) == 1) act = 1; }
+          if (RENDER && mode == MODE_RAYFWD) { if (atomicSub(q.ray_left + o, 1) == 1) act = 1; }
           else if (atomicSub(q.pending + o, 1) == 1) act = 2;
           *reinterpret_cast<volatile int*>(&S.last_flag) = act;
         }
         epi_bar_sync();
         int act = *reinterpret_cast<volatile int*>(&S.last_flag);
-        if (act == 1) {
+        if (RENDER && act == 1) {
           // every ray sample of the object has its sdf value: the per-ray scan becomes 64-ray work items of its own
           if (tid == 0) {
             const int nch = (M.n_rays + kScanChunkRays - 1) / kScanChunkRays;
@@ -846,12 +851,16 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_decoder_tc(TermArgs a) {
-  tc_body<false>(a, MegaArgs{}, SolveArgs{}, ScanArgs{});
+  tc_body<0>(a, MegaArgs{}, SolveArgs{}, ScanArgs{});
 }
-// persistent object-pipelined variant: all GN iterations of all objects in ONE launch (joint runs with or without the
-// render term, pose-only runs)
-__global__ void __launch_bounds__(kTcThreads, 1) k_gn_persistent(TermArgs a, MegaArgs q, SolveArgs sv, ScanArgs sc) {
-  tc_body<true>(a, q, sv, sc);
+// persistent object-pipelined variants: all GN iterations of all objects in ONE launch.
+// k_gn_persistent: SDF tiles only (SDF-only joint runs, pose-only runs); k_gn_persistent_render: joint runs with the
+// render term (ray-sample tiles, scan items, band tiles, SDF tiles)
+__global__ void __launch_bounds__(kTcThreads, 1) k_gn_persistent(TermArgs a, MegaArgs q, SolveArgs sv) {
+  tc_body<1>(a, q, sv, ScanArgs{});
+}
+__global__ void __launch_bounds__(kTcThreads, 1) k_gn_persistent_render(TermArgs a, MegaArgs q, SolveArgs sv, ScanArgs sc) {
+  tc_body<2>(a, q, sv, sc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1026,7 +1035,8 @@ inline int tc_setup_kernels(std::string& err) {
     err = std::string("cudaFuncSetAttribute(k_decoder_tc): ") + cudaGetErrorString(cudaGetLastError());
     return DSPGN_E_CUDA;
   }
-  if (cudaFuncSetAttribute(k_gn_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_gn_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gn_persistent_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes) != cudaSuccess) {
     err = std::string("cudaFuncSetAttribute(k_gn_persistent): ") + cudaGetErrorString(cudaGetLastError());
     return DSPGN_E_CUDA;
   }

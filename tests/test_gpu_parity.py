@@ -463,8 +463,10 @@ def test_iteration_by_iteration_vs_reference(engine, golden_dir, dec_path, cfg_k
         if not flips_ok and k_first == iters:
             k_first = k
         kk = min(k + 1, len(tr) - 1)
-        tolH = (3e-4, 6e-4)[k] if k < 2 else max(1e-3, 12 * floorH[kk])
-        toldx = (2e-5, 3e-4)[k] if k < 2 else max(1e-3, 12 * floordx[kk])
+        # the tensor-core engine's products carry ~2^-21 (3-pass split fp16) instead of 2^-24: 4x the fp32 engine's floor
+        eng = 4.0 if engine == "tc" else 1.0
+        tolH = (3e-4, 6e-4)[k] if k < 2 else max(1e-3 * eng, 12 * floorH[kk])
+        toldx = (2e-5, 3e-4)[k] if k < 2 else max(1e-3 * eng, 12 * floordx[kk])
         if k < k_first:
             assert eH < tolH and eb < 2 * tolH and edx < toldx, (k, tolH, toldx, rows)
     print(f"\n[iter-parity] {name}[{oi}] {engine}: k_first={k_first}  (k, dV, dm, relH, relb, |ddx|) = "
