@@ -201,6 +201,10 @@ struct TcSmemTail {
   int cur_class;
   int fifo[4]; int fifo_pub; int epi_seq; int last_flag;   // persistent mode: CTA-local tile FIFO (scheduler = producer warp)
   TcPlan plans[DSPGN_MAX_CLASSES];        // step plans of every decoder class (read by all warp roles)
+  // persistent mode: copies of the kernel arguments for the out-of-line solve step.  Passing references to the kernel
+  // parameters themselves would make them address-taken: the compiler then parks all of them in local memory and the tile
+  // loop reads its pointers with LDL instead of from the constant bank.
+  MegaArgs ctx_q; SolveArgs ctx_sv; int ctx_D;
 };
 constexpr size_t kTcSmemBytes = 1024 + (size_t)kTcStages * kTcStageBytes + sizeof(TcSmemTail);
 
@@ -304,7 +308,9 @@ __device__ inline void mega_push(const MegaArgs& q, int kind, int o, int n) {
 // all terms of the object's current iteration are in: solve, update, queue the next iteration (or finish).  Called by
 // the 256 epilogue threads of the CTA that completed the object's last outstanding tile.
 template <bool MEGA>
-__device__ __noinline__ void mega_solve_and_advance(const TermArgs& a, const MegaArgs& q, const SolveArgs& sv, TcSmemTail& S, int o, int tid) {
+__device__ __noinline__ void mega_solve_and_advance(TcSmemTail& S, int o, int tid) {
+  const MegaArgs& q = S.ctx_q;
+  const SolveArgs& sv = S.ctx_sv;
   __threadfence();
   SolveSmem& SM = *reinterpret_cast<SolveSmem*>(S.Jp);
   const int it = ldv(q.obj_iter + o);
@@ -317,9 +323,9 @@ __device__ __noinline__ void mega_solve_and_advance(const TermArgs& a, const Meg
     if (fin) {
       atomicAdd(q.done_objects, 1);
     } else {
-      const ObjMeta M = a.meta[o];
+      const ObjMeta M = sv.meta[o];
       const int ntS = (M.n_pts + kTcRows - 1) / kTcRows;
-      const int ntF = q.render ? (M.n_rays * a.D + kTcRows - 1) / kTcRows : 0;
+      const int ntF = q.render ? (M.n_rays * S.ctx_D + kTcRows - 1) / kTcRows : 0;
       *reinterpret_cast<volatile int*>(q.obj_iter + o) = it + 1;
       *reinterpret_cast<volatile int*>(q.pending + o) = ntS + (ntF > 0 ? 1 : 0);
       *reinterpret_cast<volatile int*>(q.ray_left + o) = ntF;
@@ -353,6 +359,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
     for (int i = 0; i < 8; ++i) mbar_init(&S.a_ready[i], 128);
     S.cur_class = -1;
     S.fifo_pub = 0; S.epi_seq = 0; S.last_flag = 0;
+    if (MEGA) { S.ctx_q = q; S.ctx_sv = sv; S.ctx_D = a.D; }
     fence_barrier_init();
   }
   if (warp == 8) tc_alloc(&S.tmem_base, 512);
@@ -509,7 +516,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
           epi_bar_sync();
           act = *reinterpret_cast<volatile int*>(&S.last_flag);
         } else act = 0;
-        if (act == 2) mega_solve_and_advance<MEGA>(a, q, sv, S, o, tid);
+        if (act == 2) mega_solve_and_advance<MEGA>(S, o, tid);
         continue;
       }
       const int o = tr.o, row0 = tr.row0, tile = tr.slot, mode = tr.mode;
@@ -840,7 +847,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
             mega_push(q, kKindScan, o, nch);
           }
         }
-        if (act == 2) mega_solve_and_advance<MEGA>(a, q, sv, S, o, tid);
+        if (act == 2) mega_solve_and_advance<MEGA>(S, o, tid);
       }
       // the next tile's prologue starts with epi_bar_sync(): Jp / rr are not rewritten before it
     }
