@@ -41,7 +41,7 @@ struct ObjState {
 
 // ---- tcgen05 engine plan (dspgn_tc.cuh): one entry per GEMM step of a tile -----------------------
 constexpr int kTcMaxSteps = 18;
-enum { TK_FWD_HIDDEN = 0, TK_FWD_LAST = 1, TK_BWD_MID = 2, TK_BWD_FIRST = 3 };
+enum { TK_FWD_HIDDEN = 0, TK_FWD_PENULT = 1, TK_BWD_MID = 2, TK_BWD_FIRST = 3 };   // PENULT: last hidden layer + the final Linear(.,1) on the CUDA cores
 struct TcStep {
   int kind;
   int n_mma;         // UMMA N (multiple of 16, <= 256)

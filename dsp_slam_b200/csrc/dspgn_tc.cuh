@@ -626,11 +626,34 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         tc_fence_after();
         if (tid == 0) DSPGN_CLK(0);
 
-        if (st.kind == TK_FWD_LAST) {
-          // ---- sdf value; seed of the backward chain (or the forward-only output) ---------------------
-          const float d0 = __uint_as_float(tc_ld1(d_t));
-          tc_wait_ld();
-          yv = tanhf(d0 + S.bias[st.layer * kHid]);                  // deep_sdf_decoder.py:107-108
+        if (st.kind == TK_FWD_PENULT) {
+          // ---- last hidden layer: bias + ReLU (mask saved), and the final Linear(width, 1) + tanh right here as a per-row
+          // dot product on the CUDA cores while the values are in registers.  As an MMA step it was the worst one: N = 16
+          // still costs the ~110-cycle floor per instruction (48 MMAs + the dependency bubble = 7.3k cycles for 256 MACs
+          // per row) and needed its own TMEM operand.  deep_sdf_decoder.py:91,103,107-108.
+          float part = 0.f;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const int u = grp + 2 * j, n0 = 32 * u;
+            uint32_t mw = 0;
+            if (n0 < st.n_mma) {
+              uint32_t v[32];
+              tc_ld32(d_t + (uint32_t)n0, v);
+              tc_wait_ld();
+              const float* bb = S.bias + st.layer * kHid + n0;
+              const float* wl = S.wlast + n0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float w = __uint_as_float(v[i]) + bb[i];
+                mw |= (w > 0.f ? 1u : 0u) << i;
+                part = fmaf(fmaxf(w, 0.f), wl[i], part);
+              }
+            }
+            S.maskw[(st.layer * 8 + u) * kTcRows + r] = mw;
+          }
+          (grp == 0 ? S.rr : S.rsc)[r] = part;             // the two column halves of the row, combined in a fixed order
+          epi_bar_sync();                                  // (also: every accumulator read of this step is finished)
+          yv = tanhf((S.rr[r] + S.rsc[r]) + S.bias[(st.layer + 1) * kHid]);      // deep_sdf_decoder.py:107-108
           if (fwd_only) {
             if (grp == 0 && r < nrows) {
               const size_t base = (mode == MODE_RAYFWD) ? (size_t)M.smp_off : (size_t)M.pts_off;
@@ -642,16 +665,14 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
             }
           }
           if (more) {
-            // the next step's MMAs overwrite accumulator column 0: both groups must have read y first
-            epi_bar_sync();
-            // g = (1 - y^2) W_last, masked by the last hidden ReLU   (written into the dead A region of this step)
+            // seed of the backward chain: g = (1 - y^2) W_last, masked by this layer's ReLU, written into the (dead) A
+            // region of this step; the first backward GEMM accumulates into the region whose reads ended at the barrier
             const float gy = 1.f - yv * yv;
-            const int ml = st.layer - 1;
 #pragma unroll 1
             for (int j = 0; j < 4; ++j) {
               const int u = grp + 2 * j, n0 = 32 * u;
               if (n0 < k_next) {
-                const uint32_t mw = S.maskw[(ml * 8 + u) * kTcRows + r];
+                const uint32_t mw = S.maskw[(st.layer * 8 + u) * kTcRows + r];
                 float t[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) t[i] = ((mw >> i) & 1u) ? gy * S.wlast[n0 + i] : 0.f;
@@ -987,11 +1008,12 @@ inline int tc_pack_decoder(const DspgnDecoderSpec& spec, const float* const* W, 
   TcPlan& P = dv->tc_plan;
   std::vector<unsigned char> blob;
   int ns = 0;
-  // forward steps: layer k, A = activations (K = in_dim), B[n][kk] = W_k[n][kk]
-  for (int k = 0; k < nl; ++k) {
+  // forward steps: layer k, A = activations (K = in_dim), B[n][kk] = W_k[n][kk].  The final Linear(width, 1) is not a
+  // GEMM step: it is folded into the epilogue of the last hidden layer (TK_FWD_PENULT) as a dot product.
+  for (int k = 0; k < nl - 1; ++k) {
     TcStep& s = P.step[ns];
     const int nin = spec.in_dim[k], nout = spec.out_dim[k];
-    s.kind = (k == nl - 1) ? TK_FWD_LAST : TK_FWD_HIDDEN;
+    s.kind = (k == nl - 2) ? TK_FWD_PENULT : TK_FWD_HIDDEN;
     s.n_mma = round16(nout);
     s.k_steps = round16(nin) / 16;
     s.a_reg = ns & 1; s.d_reg = (ns & 1) ^ 1;
@@ -1005,7 +1027,7 @@ inline int tc_pack_decoder(const DspgnDecoderSpec& spec, const float* const* W, 
   }
   P.n_fwd = ns;
   // backward steps: layer k = nl-2 .. 0, A = masked gradient (K = out_dim), B[n][kk] = W_k[kk][n]
-  int a_reg = P.step[ns - 1].a_reg;          // the seed overwrites the (dead) A operand of the last forward step
+  int a_reg = P.step[ns - 1].a_reg;          // the seed overwrites the (dead) A operand of the last forward GEMM step
   for (int k = nl - 2; k >= 0; --k) {
     TcStep& s = P.step[ns];
     const int nin = spec.in_dim[k], nout = spec.out_dim[k];
