@@ -566,6 +566,7 @@ int launch_init(DspgnSolver* s, int pose_only, bool mega = false, bool render = 
   ia.pt_active = nullptr; ia.n_obj = s->n_obj; ia.code_len = s->cfg.code_len; ia.D = s->cfg.num_depth_samples;
   ia.pose_only = pose_only;
   ia.gather = s->gdev; ia.results = s->d_results.as<float>(); ia.n_bad = s->n_bad;
+  ia.decs = s->d_decs.as<DecoderDev>();
   ia.mega = mega ? 1 : 0;
   if (mega) {
     ia.render = render ? 1 : 0;
@@ -649,6 +650,7 @@ SolveArgs base_solve(DspgnSolver* s, int pose_only) {
   v.prm = SolverParams{c.k1, c.k2, c.k3, c.k4, c.b1, c.b2, c.lr, c.s_damp, c.code_len, c.num_depth_samples, c.cut_off, c.sdf_only};
   v.n_obj = s->n_obj; v.pose_only = pose_only; v.results = s->d_results.as<float>();
   v.gather = s->gdev;
+  v.decs = s->d_decs.as<DecoderDev>();
   v.dbg_obj = -1; v.dbg_H = nullptr; v.dbg_b = nullptr; v.dbg_dx = nullptr; v.dbg_loss = nullptr;
   v.dbg_clk = s->clk_on ? s->d_clk.as<long long>() + kClkTiles * kTcMaxSteps * kClkSlots : nullptr;
   return v;

@@ -37,6 +37,10 @@ struct ObjState {
   int iters;
   int V, m;                    // last render counters
   int n_active;                // pose-only inlier count (optimizer.py:76-78)
+  // layer 0 with the latent part folded: zb0[j] = b0[j] + sum_i W0[j][i] z[i]  (i < latent size), refreshed whenever z
+  // changes (k_init, end of the solve step).  The tensor-core engine then needs only the 3 xyz columns of layer 0 per
+  // point, which it evaluates on the CUDA cores while building the first GEMM operand.
+  float zb0[256];
 };
 
 // ---- tcgen05 engine plan (dspgn_tc.cuh): one entry per GEMM step of a tile -----------------------

@@ -124,7 +124,19 @@ struct InitArgs {
   GatherDev gather;
   float* results;          // records of objects rejected at upload are written here
   int n_bad;
+  const DecoderDev* decs;  // layer-0 fold (ObjState.zb0)
 };
+
+// zb0 = b0 + W0[:, :L] z   (fp32 FMA chain in i order; all threads of the calling CTA / epilogue)
+__device__ __forceinline__ void refresh_zb0(ObjState& st, const DecoderDev& dec, int tid, int nthreads) {
+  const float* __restrict__ W = dec.Wf[0];      // reduction-major [in][256]
+  const float* __restrict__ b = dec.bias[0];
+  for (int j = tid; j < kHid; j += nthreads) {
+    float acc = b[j];
+    for (int i = 0; i < dec.L; ++i) acc = fmaf(W[i * kHid + j], ldv(&st.z[i]), acc);
+    st.zb0[j] = acc;
+  }
+}
 
 __global__ void k_init(InitArgs a) {
   const int o = blockIdx.x, tid = threadIdx.x;
@@ -147,6 +159,8 @@ __global__ void k_init(InitArgs a) {
     a.V_count[o] = 0;
     a.band_m[o] = 0;
   }
+  __syncthreads();
+  refresh_zb0(st, a.decs[M.class_id], tid, blockDim.x);
   if (M.bad) {                               // rejected at upload: no tile, no solve -- its record is final now
     __syncthreads();
     if (tid == 0) write_record(a.results, a.gather, o, st, a.pose_only, M.scale);
@@ -179,6 +193,7 @@ struct SolveArgs {
   int last_iter;          // write the result record
   int iter_index;
   float* results;         // [n_obj][DSPGN_RESULT_FLOATS]
+  const DecoderDev* decs; // layer-0 fold (ObjState.zb0) is refreshed when the code changes
   GatherDev gather;       // optional: the record also goes straight into rank 0's HBM (peer store over NVLink)
   // debug: dump the system of object dbg_obj and do not update any state
   int dbg_obj; float* dbg_H; float* dbg_b; float* dbg_dx; float* dbg_loss;
@@ -460,6 +475,7 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
   const bool fail = (s_flag != 0);
   if (!a.pose_only && tid < L && !fail) st.z[tid] = ldv(&st.z[tid]) + prm.lr * xs[tid + 7];
   solve_sync<MEGA>();                        // the result record below reads every z entry
+  if (!a.pose_only && !fail && !last_iter) refresh_zb0(st, a.decs[a.meta[o].class_id], tid, kSolveThreads);
   if (tid == 0) {
     st.loss = loss; st.V = V; st.m = m;
     a.V_count[o] = 0;

@@ -230,10 +230,13 @@ __device__ __forceinline__ void store_a_unit(uint32_t taddr, const float (&t)[32
 }
 
 // signal "unit u of the next A operand is in TMEM" (or simply "done with this unit")
+// (one arrival per warp: 4 per unit instead of 128 -- the 128 individual arrivals on one mbarrier serialised for
+//  several hundred cycles on the path that decides when the next layer's first MMA can issue)
 __device__ __forceinline__ void unit_done(uint64_t* bar) {
   tc_wait_st();
   tc_fence_before();
-  mbar_arrive(bar);
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 
 struct TileRef { int o, row0, slot, mode, tile; };
@@ -356,7 +359,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
   if (tid == 0) {
     for (int i = 0; i < kTcStages; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
     mbar_init(&S.acc_full[0], 1);
-    for (int i = 0; i < 8; ++i) mbar_init(&S.a_ready[i], 128);
+    for (int i = 0; i < 8; ++i) mbar_init(&S.a_ready[i], 4);
     S.cur_class = -1;
     S.fifo_pub = 0; S.epi_seq = 0; S.last_flag = 0;
     if (MEGA) { S.ctx_q = q; S.ctx_sv = sv; S.ctx_D = a.D; }
@@ -542,6 +545,9 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         for (int i = tid; i < kHid; i += kTcEpiThreads) S.wlast[i] = dec.w_last[i];
       }
       if (tid < kMaxCode + 16) S.zs[tid] = (tid < L) ? ldv(&ost.z[tid]) : 0.f;
+      // layer 0 with the latent part folded into a per-object bias (ObjState.zb0, refreshed by k_init / the solve step);
+      // written after the per-class reload above, read after the barrier below
+      S.bias[tid] = ldv(&ost.zb0[tid]);
       // pose-only inlier cut (optimizer.py:76-78): recorded while iteration `cut_iter` runs, applied afterwards
       const uint8_t* mask_in = a.pt_active;
       uint8_t* mask_out = a.pt_active_out;
@@ -596,19 +602,37 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         return (j < 0) ? S.zs[i] : ((unsigned)j < 3u ? S.xr[j * kTcRows + r] : 0.f);
       };
 
-      // ---- A operand of step 0: the decoder input, K padded to k_steps*16 ---------------------------
+      // ---- A operand of the first GEMM step (= layer 1): layer 0 on the CUDA cores.  With W0[:, :L] z folded into
+      // zb0, layer 0 is 3 FMAs per output:  h0[j] = relu(zb0[j] + W0[j][L..L+2] . x)  (deep_sdf_decoder.py:91,103).
+      // As a GEMM step (K = 80) it cost 4.8k cycles per tile, most of it the dependency bubble. --------------------
       {
         const TcStep s0 = plan.step[0];
         const uint32_t a_t = tmem + (uint32_t)s0.a_reg * 256u + lane_addr;
         const int kk = s0.k_steps * 16;
+        const int n0out = dec.out_dim[0];
+        const float* __restrict__ w0x = dec.Wf[0] + (size_t)L * kHid;      // rows L..L+2 of the reduction-major layer-0 matrix
+        const float px = x0, py = x1, pz = x2;
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           const int u = grp + 2 * j, n0 = 32 * u;
           if (n0 < kk) {
             float t[32];
+            uint32_t mw = 0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = inp(n0 + i);
+            for (int i = 0; i < 32; ++i) {
+              const int c = n0 + i;
+              float w = S.bias[c];
+              w = fmaf(__ldg(w0x + c), px, w);
+              w = fmaf(__ldg(w0x + kHid + c), py, w);
+              w = fmaf(__ldg(w0x + 2 * kHid + c), pz, w);
+              const bool on = (c < n0out) && (w > 0.f);
+              mw |= (on ? 1u : 0u) << i;
+              t[i] = on ? w : 0.f;
+            }
+            S.maskw[(0 * 8 + u) * kTcRows + r] = mw;
             store_a_unit(a_t + (uint32_t)n0, t);
+          } else {
+            S.maskw[(0 * 8 + u) * kTcRows + r] = 0u;
           }
           unit_done(&S.a_ready[u]);
         }
@@ -1010,7 +1034,10 @@ inline int tc_pack_decoder(const DspgnDecoderSpec& spec, const float* const* W, 
   int ns = 0;
   // forward steps: layer k, A = activations (K = in_dim), B[n][kk] = W_k[n][kk].  The final Linear(width, 1) is not a
   // GEMM step: it is folded into the epilogue of the last hidden layer (TK_FWD_PENULT) as a dot product.
-  for (int k = 0; k < nl - 1; ++k) {
+  // Layer 0 is no GEMM step either: with its latent part folded into a per-object bias (ObjState.zb0) it is 3 FMAs per
+  // output and is evaluated while the first operand is built (tc_body prologue).
+  if (nl < 4 || li == 1) return 0;          // needs a hidden GEMM layer after layer 0 and no concat at layer 1
+  for (int k = 1; k < nl - 1; ++k) {
     TcStep& s = P.step[ns];
     const int nin = spec.in_dim[k], nout = spec.out_dim[k];
     s.kind = (k == nl - 2) ? TK_FWD_PENULT : TK_FWD_HIDDEN;

@@ -71,17 +71,20 @@ def all_gather_records(local, n_total, world_size, rank, order, bounds, group=No
 def records_to_results(rec, code_len):
     """(n, RESULT_FLOATS) float32 numpy -> list of dicts like Optimizer.reconstruct_batch returns."""
     from .optimizer import ResultDict
-    rec = np.ascontiguousarray(rec, dtype=np.float32)
+    rec = np.array(rec, dtype=np.float32, order="C")           # one private copy; the per-object arrays are views of it
     ints = rec.view(np.int32)
+    status = ints[:, 81].tolist()
+    loss = rec[:, 80].tolist()
+    nv, nb = ints[:, 82].tolist(), ints[:, 83].tolist()
+    T = rec[:, :16].reshape(-1, 4, 4)
+    Z = rec[:, 16:16 + code_len]
     out = []
-    for i in range(rec.shape[0]):
-        status = int(ints[i, 81])
-        if status != 0:
-            out.append(ResultDict(t_cam_obj=None, code=None, is_good=False, loss=float(rec[i, 80]), status=status))
+    for i, st in enumerate(status):
+        if st != 0:
+            out.append(ResultDict(t_cam_obj=None, code=None, is_good=False, loss=loss[i], status=st))
         else:
-            out.append(ResultDict(t_cam_obj=rec[i, :16].reshape(4, 4).copy(), code=rec[i, 16:16 + code_len].copy(),
-                                  is_good=True, loss=float(rec[i, 80]), status=0,
-                                  n_valid=int(ints[i, 82]), n_band=int(ints[i, 83])))
+            out.append(ResultDict(t_cam_obj=T[i], code=Z[i], is_good=True, loss=loss[i], status=0,
+                                  n_valid=nv[i], n_band=nb[i]))
     return out
 
 

@@ -246,16 +246,9 @@ def _records(out, n):
 
 
 def _unpack_all(out, n, code_len):
-    rec, ints = _records(out, n)
-    res = []
-    for i in range(n):
-        status = int(ints[i, 81])
-        if status != _lib.ST_OK:
-            res.append(ResultDict(t_cam_obj=None, code=None, is_good=False, loss=float(rec[i, 80]), status=status))
-        else:
-            res.append(ResultDict(t_cam_obj=rec[i, :16].reshape(4, 4), code=rec[i, 16:16 + code_len], is_good=True,
-                                  loss=float(rec[i, 80]), status=0, n_valid=int(ints[i, 82]), n_band=int(ints[i, 83])))
-    return res
+    from .distributed import records_to_results
+    rec, _ = _records(out, n)
+    return records_to_results(rec, code_len)
 
 
 class Optimizer(object):
