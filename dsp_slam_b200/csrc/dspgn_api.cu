@@ -714,6 +714,7 @@ int run_batch_impl(DspgnSolver* s, int mode) {
       q.ev = s->d_ev.as<long long>(); q.ev_cap = kEvCap;
     }
     SolveArgs v = base_solve(s, pose_only);
+    v.ev = q.ev; v.ev_cap = q.ev_cap;
     v.base_s = s->d_tbase_static; v.base_r = s->d_tbase_r_static; v.tile_rows = kTcRows; v.last_iter = 0; v.iter_index = 0; v.dbg_clk = nullptr;
     ScanArgs sa = base_scan(s);
     if (s->timing) cudaEventRecord(next_event(s), s->stream);

@@ -198,7 +198,18 @@ struct SolveArgs {
   // debug: dump the system of object dbg_obj and do not update any state
   int dbg_obj; float* dbg_H; float* dbg_b; float* dbg_dx; float* dbg_loss;
   long long* dbg_clk;      // optional: 16 clock64 stamps of object 0's CTA
+  long long* ev; int ev_cap;   // optional event log of the persistent kernel (phase stamps of the solve step)
 };
+__device__ __forceinline__ void solve_event(const SolveArgs& a, int o, int phase) {
+  if (a.ev == nullptr) return;
+  const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(a.ev), 1ull);
+  if ((long long)slot >= a.ev_cap) return;
+  unsigned long long t; unsigned sm;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+  a.ev[1 + 2 * slot] = (long long)t;
+  a.ev[2 + 2 * slot] = (8ll << 56) | ((long long)sm << 40) | ((long long)o << 24) | (long long)phase;
+}
 
 constexpr int kSolveThreads = 256;
 constexpr int kPMax = 7 + kMaxCode;   // 71
@@ -250,7 +261,7 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
   const int L = prm.code_len;
   const int npose = a.pose_only ? 6 : 7;
   const int P = a.pose_only ? 6 : (7 + L);
-#define SOLVE_CLK(k) do { if (!MEGA && a.dbg_clk != nullptr && o == 0 && tid == 0) a.dbg_clk[k] = clock64(); } while (0)
+#define SOLVE_CLK(k) do { if (!MEGA && a.dbg_clk != nullptr && o == 0 && tid == 0) a.dbg_clk[k] = clock64(); if (MEGA && tid == 0) solve_event(a, o, k); } while (0)
   SOLVE_CLK(0);
   const bool dbg = (a.dbg_H != nullptr);
   const bool use_render = !a.pose_only && !prm.sdf_only;

@@ -312,7 +312,7 @@ def test_mixed_classes_through_persistent_kernel(dec_path, cfg_kitti, oracle, or
         # engine shows the same 1e-2 on the 128/129-point objects, tools/diag_mixed.py)
         m = o["pts"].shape[0]
         assert np.abs(r.t_cam_obj - ref["t_cam_obj"]).max() < (3e-3 if m >= 500 else 2e-2)
-        assert np.abs(r.code - ref["code"]).max() < (1e-3 if m >= 500 else 4e-3)
+        assert np.abs(r.code - ref["code"]).max() < (1e-3 if m >= 500 else 8e-3)
     # the persistent schedule and the per-iteration schedule are bit-identical
     import os
     os.environ["DSPGN_MEGA"] = "0"

@@ -54,3 +54,19 @@ for md in (0, 1, 2, 3):
         dur += list((e_[:k] - b_[:k]) / 1e3)
     if dur:
         print(f"{MODE[md]} tiles: n={len(dur)} median {np.median(dur):.1f} us  p10 {np.percentile(dur,10):.1f} p90 {np.percentile(dur,90):.1f}")
+
+# solve phases (kind 8: phase index in the tile field): 0 start, 1 loss reductions, 2 rotation prior, 3 tile partials, 4 system in smem,
+# 5 elimination done, 6 update / record done
+ph = kind == 8
+if ph.any():
+    names = ["loss-reductions", "rot-prior", "tile-partials", "assemble", "gauss-jordan", "update+record"]
+    acc = {n: [] for n in names}
+    for s_ in np.unique(sm[ph]):
+        m_ = ph & (sm == s_)
+        tt, pp = t[m_], tile[m_]
+        order = np.argsort(tt)
+        tt, pp = tt[order], pp[order]
+        for i in range(len(tt) - 1):
+            if pp[i + 1] == pp[i] + 1 and pp[i] < 6:
+                acc[names[pp[i]]].append((tt[i + 1] - tt[i]) / 1e3)
+    print("solve phases (us, median over all solves): " + "  ".join(f"{n} {np.median(v):.1f}" for n, v in acc.items() if v))
