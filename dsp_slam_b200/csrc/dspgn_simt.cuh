@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decoder_simt(TermArgs a) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           const int r = 4 * bi + u, c = 4 * bj + v;
-          if (c >= r && c < kMaxCode + 7) accp[r * kPInt + c] = h[u][v];
+          if (c >= r && c < kMaxCode + 7) accp[tri_index(r, c)] = h[u][v];
         }
     } else if (tid < 171 + kMaxCode + 7) {
       const int c = tid - 171;

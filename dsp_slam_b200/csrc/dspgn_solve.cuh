@@ -214,7 +214,7 @@ __device__ __forceinline__ void solve_event(const SolveArgs& a, int o, int phase
 constexpr int kSolveThreads = 256;
 constexpr int kPMax = 7 + kMaxCode;   // 71
 constexpr int kAsStride = kPMax + 2;  // 73 floats: odd stride -> thread-per-row reads are bank-conflict free
-constexpr int kMaxEnt = (kPMax * (kPMax + 1) / 2 + kPMax + kSolveThreads - 1) / kSolveThreads;   // 11
+constexpr int kMaxEnt = (kTriInt + kPInt + kSolveThreads - 1) / kSolveThreads;   // 11 entries of a tile partial per thread
 
 __device__ __forceinline__ int ext_to_int(int e, int npose, int L) {
   // external order [pose | code]  ->  internal rows [code 0..63 | pose 64..70]
@@ -342,24 +342,34 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
   // ---- assemble the lower triangle of H and the b row (optimizer.py:161-184; pose-only: :68-71) ----
   const double wS = a.pose_only ? 1.0 / nS : (double)prm.k2 / nS;
   const double wR = use_render ? (double)prm.k1 / (double)m : 0.0;
-  const int nTri = P * (P + 1) / 2, nEnt = nTri + P;
+  // Entry e = tid + q*256 of a tile partial: e < kTriInt -> packed upper-triangle element (r, c) of the internal matrix,
+  // then the 72 b entries.  Consecutive threads read consecutive floats.  (i, j) = position in the EXTERNAL system
+  // [pose | code] with i >= j, i == P for a right-hand-side entry, i = -1 for an entry that is not part of this system
+  // (padding column 71, code rows >= code_len, every code row in a pose-only run).
+  auto int_to_ext = [&](int r) -> int {
+    if (r >= kMaxCode) { const int p = r - kMaxCode; return (p < npose) ? p : -1; }
+    return (!a.pose_only && r < L) ? npose + r : -1;
+  };
   int ei[kMaxEnt], ej[kMaxEnt], eidx[kMaxEnt];
   double accv[kMaxEnt], accr[kMaxEnt];
 #pragma unroll
   for (int q = 0; q < kMaxEnt; ++q) {
     const int e = tid + q * kSolveThreads;
     int i = -1, j = 0, idx = 0;
-    if (e < nTri) {
-      i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
-      while ((i + 1) * (i + 2) / 2 <= e) ++i;
-      while (i * (i + 1) / 2 > e) --i;
-      j = e - i * (i + 1) / 2;
-      int ri = ext_to_int(i, npose, L), ci = ext_to_int(j, npose, L);
-      if (ri > ci) { int t = ri; ri = ci; ci = t; }        // partials hold the upper triangle
-      idx = ri * kPInt + ci;
-    } else if (e < nEnt) {
-      i = P; j = e - nTri;
-      idx = kAccB + ext_to_int(j, npose, L);
+    if (e < kTriInt) {
+      // invert tri_index: base(r) = r (145 - r) / 2 <= e
+      int r = (int)((145.f - sqrtf(21025.f - 8.f * (float)e)) * 0.5f);
+      r = max(0, min(r, kPInt - 1));
+      while (r + 1 < kPInt && tri_index(r + 1, r + 1) <= e) ++r;
+      while (tri_index(r, r) > e) --r;
+      const int c = r + (e - tri_index(r, r));
+      const int xi = int_to_ext(r), xj = int_to_ext(c);
+      if (xi >= 0 && xj >= 0) { i = max(xi, xj); j = min(xi, xj); }
+      idx = e;
+    } else if (e < kTriInt + kPInt) {
+      const int xj = int_to_ext(e - kTriInt);
+      if (xj >= 0) { i = P; j = xj; }
+      idx = kAccB + (e - kTriInt);
     }
     ei[q] = i; ej[q] = j; eidx[q] = idx;
     accv[q] = 0.0; accr[q] = 0.0;

@@ -847,7 +847,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             const int rI = 4 * bi + u, cI = 4 * bj + v;
-            if (cI >= rI && cI < kMaxCode + 7) accp[rI * kPInt + cI] = h[u][v];
+            if (cI >= rI && cI < kMaxCode + 7) accp[tri_index(rI, cI)] = h[u][v];
           }
       } else if (tid < 171 + kMaxCode + 7) {
         const int c = tid - 171;
