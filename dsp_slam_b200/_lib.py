@@ -43,7 +43,9 @@ class ObjectIn(C.Structure):
                 ("pts", _FP), ("n_pts", C.c_int32), ("pts_rs", C.c_int32), ("pts_cs", C.c_int32),
                 ("rays", _FP), ("n_rays", C.c_int32), ("rays_rs", C.c_int32), ("rays_cs", C.c_int32),
                 ("depth", _FP), ("n_depth", C.c_int32),
-                ("code", _FP), ("scale", C.c_float), ("class_id", C.c_int32)]
+                ("code", _FP), ("scale", C.c_float), ("class_id", C.c_int32),
+                ("pixels", _FP), ("pix_rs", C.c_int32), ("pix_cs", C.c_int32),
+                ("inv_k", _FP), ("t_cam_world", _FP)]
 
 
 class ObjectOut(C.Structure):
@@ -99,6 +101,7 @@ SYMBOLS = [
     ("dspgn_debug_system", C.c_int, [_VP, C.c_int, C.c_int, _FP, _FP, _FP, _FP, _FP, _FP]),
     ("dspgn_debug_system_iter", C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _FP, _FP, _FP, _FP, _FP, _FP]),
     ("dspgn_debug_clocks", C.c_int, [_VP, C.POINTER(C.c_longlong), C.c_int]),
+    ("dspgn_debug_inputs", C.c_int, [_VP, C.c_int, _FP, _FP, _FP]),
     ("dspgn_debug_events", C.c_int, [_VP, C.POINTER(C.c_longlong), C.c_int]),
     ("dspgn_tc_selftest", C.c_int, [C.c_int, C.c_int, C.c_int, _FP, _FP, _FP]),
 ]

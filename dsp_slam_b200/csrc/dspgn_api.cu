@@ -399,7 +399,7 @@ int upload_batch_impl(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, bool d
   const int D = s->cfg.num_depth_samples;
   s->h_meta.assign(n_obj, ObjMeta{});
   long long tp = 0, tr = 0, tf = 0, ts = 0;
-  int max_rays = 0, n_bad = 0;
+  int max_rays = 0, n_bad = 0, any_build = 0;
   for (int o = 0; o < n_obj; ++o) {
     const DspgnObjectIn& I = in[o];
     // misuse of the API fails the call; an unusable DETECTION only fails that object (status BAD_INPUT ->
@@ -408,11 +408,14 @@ int upload_batch_impl(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, bool d
     if (!I.t_cam_obj) return fail(DSPGN_E_ARG, "object without a pose");
     if (I.class_id < 0 || I.class_id >= (int)s->classes.size()) return fail(DSPGN_E_ARG, "bad class_id");
     const bool bad = I.n_pts < 1 || !I.pts || I.n_rays < 0 || I.n_depth < 0 || I.n_depth > I.n_rays ||
-                     I.n_rays > kScanMaxRays || (I.n_rays > 0 && I.n_depth > 0 && !I.depth);
+                     I.n_rays > kScanMaxRays || (I.n_rays > 0 && I.n_depth > 0 && !I.depth) || (I.pixels && !I.inv_k);
+    const float* ray_src = I.pixels ? I.pixels : I.rays;
     ObjMeta& M = s->h_meta[o];
     M.bad = bad ? 1 : 0;
     M.pts_off = (int)tp; M.n_pts = bad ? 0 : I.n_pts;
-    M.ray_off = (int)tr; M.n_rays = (!bad && I.rays) ? I.n_rays : 0; M.n_fg = (!bad && I.rays) ? I.n_depth : 0;
+    M.ray_off = (int)tr; M.n_rays = (!bad && ray_src) ? I.n_rays : 0; M.n_fg = (!bad && ray_src) ? I.n_depth : 0;
+    M.build = bad ? 0 : ((I.pixels ? 1 : 0) | (I.t_cam_world ? 2 : 0));
+    any_build |= M.build;
     M.fg_off = (int)tf; M.smp_off = (int)ts;
     M.class_id = I.class_id; M.scale = I.scale; M.has_code = I.code != nullptr;
     tp += M.n_pts; tr += M.n_rays; tf += M.n_fg; ts += (long long)M.n_rays * D;
@@ -426,7 +429,8 @@ int upload_batch_impl(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, bool d
   const size_t o_meta = 0, o_T = al(o_meta + sizeof(ObjMeta) * n_obj), o_code = al(o_T + 64 * n_obj),
                o_pts = al(o_code + 4 * kMaxCode * (size_t)n_obj), o_rays = al(o_pts + 12 * (size_t)tp),
                o_depth = al(o_rays + 12 * (size_t)tr), o_tb = al(o_depth + 4 * (size_t)tf),
-               total = al(o_tb + 3 * 4 * (size_t)n_obj);
+               o_aux = al(o_tb + 3 * 4 * (size_t)n_obj),
+               total = al(o_aux + (any_build ? 4 * (size_t)kAuxFloats * n_obj : 0));
   if (s->upload_pending) { CU(cudaEventSynchronize(s->ev_upload)); s->upload_pending = false; }
   if (s->d_stage.cap < total) CU(cudaStreamSynchronize(s->stream));      // kernels of an earlier batch may still read the old block
   if (s->h_stage.reserve(total) || s->d_stage.reserve(total)) return fail(DSPGN_E_ALLOC, "staging allocation failed");
@@ -464,14 +468,34 @@ int upload_batch_impl(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, bool d
     else for (int r = 0; r < M.n_pts; ++r)
       for (int c = 0; c < 3; ++c) p[3 * (size_t)r + c] = I.pts[(size_t)r * I.pts_rs + (size_t)c * I.pts_cs];
     float* q = hR + 3 * (size_t)M.ray_off;
+    if (M.build & 1) {                      // pixel coordinates: the device turns (u, v, 1) into inv_k [u, v, 1]
+      for (int r = 0; r < M.n_rays; ++r) {
+        q[3 * (size_t)r] = I.pixels[(size_t)r * I.pix_rs]; q[3 * (size_t)r + 1] = I.pixels[(size_t)r * I.pix_rs + I.pix_cs];
+        q[3 * (size_t)r + 2] = 1.f;
+      }
+    } else
     for (int r = 0; r < M.n_rays; ++r)
       for (int c = 0; c < 3; ++c) q[3 * (size_t)r + c] = I.rays[(size_t)r * I.rays_rs + (size_t)c * I.rays_cs];
+    if (any_build) {
+      float* ax = reinterpret_cast<float*>(hb + o_aux) + (size_t)o * kAuxFloats;
+      for (int i = 0; i < kAuxFloats; ++i) ax[i] = 0.f;
+      if (M.build & 1) for (int i = 0; i < 9; ++i) ax[i] = I.inv_k[i];
+      if (M.build & 2) for (int i = 0; i < 12; ++i) ax[9 + i] = I.t_cam_world[i];
+    }
     if (M.n_fg) memcpy(hD + M.fg_off, I.depth, 4 * (size_t)M.n_fg);
   }
   CU(cudaMemcpyAsync(s->d_stage.p, hb, total, cudaMemcpyHostToDevice, s->stream));
   CU(cudaEventRecord(s->ev_upload, s->stream));
   s->upload_pending = true;
   unsigned char* db = s->d_stage.as<unsigned char>();
+  if (any_build) {                          // rays from pixels / world points -> camera frame, once per upload, in place
+    BuildArgs ba{};
+    ba.meta = reinterpret_cast<ObjMeta*>(db + o_meta); ba.T_init = reinterpret_cast<float*>(db + o_T);
+    ba.pts = reinterpret_cast<float*>(db + o_pts); ba.rays = reinterpret_cast<float*>(db + o_rays);
+    ba.aux = reinterpret_cast<const float*>(db + o_aux); ba.n_obj = n_obj;
+    k_build_inputs<<<n_obj, 256, 0, s->stream>>>(ba);
+    CU(cudaGetLastError());
+  }
   s->d_meta = reinterpret_cast<ObjMeta*>(db + o_meta);
   s->d_Tinit = reinterpret_cast<float*>(db + o_T);
   s->d_code = reinterpret_cast<float*>(db + o_code);
@@ -1062,6 +1086,17 @@ int dspgn_debug_clocks(DspgnSolver* s, long long* out, int n) {
   CU(cudaSetDevice(s->device));
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaMemcpy(out, s->d_clk.p, sizeof(long long) * (size_t)std::min(n, have), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int dspgn_debug_inputs(DspgnSolver* s, int obj, float* t_cam_obj, float* pts, float* rays) {
+  if (!s || obj < 0 || obj >= s->n_obj) return fail(DSPGN_E_ARG, "bad argument");
+  CU(cudaSetDevice(s->device));
+  CU(cudaStreamSynchronize(s->stream));
+  const ObjMeta& M = s->h_meta[obj];
+  if (t_cam_obj) CU(cudaMemcpy(t_cam_obj, s->d_Tinit + 16 * (size_t)obj, 64, cudaMemcpyDeviceToHost));
+  if (pts && M.n_pts) CU(cudaMemcpy(pts, s->d_pts + 3 * (size_t)M.pts_off, 12 * (size_t)M.n_pts, cudaMemcpyDeviceToHost));
+  if (rays && M.n_rays) CU(cudaMemcpy(rays, s->d_rays + 3 * (size_t)M.ray_off, 12 * (size_t)M.n_rays, cudaMemcpyDeviceToHost));
   return 0;
 }
 

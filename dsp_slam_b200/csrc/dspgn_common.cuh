@@ -30,6 +30,7 @@ struct ObjMeta {
   float scale;                 // estimate_pose only
   int has_code;
   int bad;                     // unusable detection, rejected at upload: status DSPGN_ST_BAD_INPUT, never evaluated
+  int build;                   // device-side input construction: bit 0 rays from pixels (invK), bit 1 world points / world pose (T_cw)
 };
 
 // Evolving per-object GN state (device resident for all iterations).

@@ -109,6 +109,49 @@ __device__ inline void write_record(float* results, const GatherDev& g, int o, c
   }
 }
 
+// ---- device-side input construction --------------------------------------------------------------
+// Runs once per upload, in place on the uploaded staging block: ray slots hold (u, v, 1) and become inv_k [u, v, 1]
+// (loss_utils.py:23-37 / LocalMapping_util.cc:378-386); world map points become camera points x_c = R x_w + t
+// (LocalMapping_util.cc:344-352) and the object's world pose is composed with the camera pose, T_co = T_cw T_wo (:390).
+// aux[o]: inv_k (9, row-major) | T_cw (12, rows of [R|t]).
+struct BuildArgs { const ObjMeta* meta; float* T_init; float* pts; float* rays; const float* aux; int n_obj; };
+constexpr int kAuxFloats = 24;
+__global__ void k_build_inputs(BuildArgs a) {
+  const int o = blockIdx.x, tid = threadIdx.x;
+  const ObjMeta M = a.meta[o];
+  if (M.build == 0) return;
+  const float* ax = a.aux + (size_t)o * kAuxFloats;
+  if (M.build & 1) {
+    float K[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) K[i] = ax[i];
+    for (int i = tid; i < M.n_rays; i += blockDim.x) {
+      float* r = a.rays + 3 * (size_t)(M.ray_off + i);
+      const float u = r[0], v = r[1];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) r[k] = __fadd_rn(__fmaf_rn(K[3 * k + 1], v, __fmul_rn(K[3 * k], u)), K[3 * k + 2]);
+    }
+  }
+  if (M.build & 2) {
+    float T[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T[i] = ax[9 + i];
+    for (int i = tid; i < M.n_pts; i += blockDim.x) {
+      float* p = a.pts + 3 * (size_t)(M.pts_off + i);
+      float x, y, z;
+      xform_point(T, p[0], p[1], p[2], x, y, z);
+      p[0] = x; p[1] = y; p[2] = z;
+    }
+    if (tid == 0) {
+      float* Tw = a.T_init + 16 * (size_t)o;
+      float B[12], C[12];
+      for (int i = 0; i < 12; ++i) B[i] = Tw[i];
+      mul_affine(T, B, C);
+      for (int i = 0; i < 12; ++i) Tw[i] = C[i];
+    }
+  }
+}
+
 struct InitArgs {
   const ObjMeta* meta;
   ObjState* state;

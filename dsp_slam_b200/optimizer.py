@@ -135,7 +135,25 @@ class BatchSolver:
         rec["scale"] = 1.0
         code_len = self.cfg.code_len
         for i, o in enumerate(objs):                       # optional members
-            R = o.get("rays")
+            px = o.get("pixels")
+            if px is not None and len(px):
+                # rays built on the device: rays = inv_k [u, v, 1] (loss_utils.get_rays, reconstruct/loss_utils.py:23-37)
+                px = _as32(px)
+                Kinv = np.ascontiguousarray(o["inv_k"], dtype=np.float32).reshape(3, 3)
+                D = o.get("depth")
+                D = np.ascontiguousarray(D if D is not None else np.zeros(0), dtype=np.float32).reshape(-1)
+                rec["pixels"][i] = px.ctypes.data; rec["n_rays"][i] = px.shape[0]
+                rec["pix_rs"][i] = px.strides[0] >> 2; rec["pix_cs"][i] = px.strides[1] >> 2
+                rec["inv_k"][i] = Kinv.ctypes.data
+                rec["depth"][i] = D.ctypes.data; rec["n_depth"][i] = D.shape[0]
+                keep.append((px, Kinv, D))
+            Tcw = o.get("t_cam_world")
+            if Tcw is not None:
+                # pts are WORLD map points and t_cam_obj the object's WORLD pose (src/LocalMapping_util.cc:344-352,390)
+                Tcw = np.ascontiguousarray(Tcw, dtype=np.float32).reshape(4, 4)
+                rec["t_cam_world"][i] = Tcw.ctypes.data
+                keep.append(Tcw)
+            R = o.get("rays") if px is None or not len(px) else None
             if R is not None and len(R):
                 R = _as32(R)
                 D = o.get("depth")

@@ -110,6 +110,15 @@ typedef struct {
   const float* code;                                    /* (code_len,) initial code or NULL = zeros */
   float scale;                                          /* estimate_pose only: object scale */
   int32_t class_id;                                     /* index into the solver's decoder list */
+  /* Optional input construction ON THE DEVICE; all NULL = the arrays above are used as given.
+   *   pixels + inv_k   rays[i] = inv_k [u_i, v_i, 1]   (loss_utils.get_rays, reconstruct/loss_utils.py:23-37;
+   *                    src/LocalMapping_util.cc:378-386).  (n_rays,2) pixel coordinates replace `rays` (ignored).
+   *   t_cam_world      SE(3) world->camera, 4x4 row-major: `pts` are WORLD map points, x_c = R x_w + t
+   *                    (LocalMapping_util.cc:344-352), and `t_cam_obj` is the object's WORLD pose T_wo:
+   *                    T_co = T_cw T_wo (LocalMapping_util.cc:390). */
+  const float* pixels; int32_t pix_rs, pix_cs;
+  const float* inv_k;                                   /* 3x3 row-major */
+  const float* t_cam_world;                             /* 4x4 row-major */
 } DspgnObjectIn;
 
 typedef struct {
@@ -222,6 +231,10 @@ int dspgn_debug_system_iter(DspgnSolver* s, int obj, int mode, int iter, float* 
 /* Debug: clock64 timeline of CTA 0 of the tensor-core decoder kernel, [4 tiles][18 steps][8 slots]
  * (only when the solver was created with env DSPGN_CLK set). */
 int dspgn_debug_clocks(DspgnSolver* s, long long* out, int n);
+
+/* Test hook for the device-side input construction: the resident batch's object `obj` as the kernels see it --
+ * t_cam_obj (16, row-major), pts (n_pts*3, xyz interleaved), rays (n_rays*3).  Any pointer may be NULL. */
+int dspgn_debug_inputs(DspgnSolver* s, int obj, float* t_cam_obj, float* pts, float* rays);
 
 /* Debug: event log of the last persistent-kernel run (tile begin/end per kind, scan, solve, queue pops), enabled by
  * env DSPGN_CLK at solver creation; returns the number of (timestamp, descriptor) pairs written, or a negative code. */

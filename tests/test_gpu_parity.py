@@ -674,3 +674,45 @@ def test_decoder_variants_layernorm_xyz_in_all_use_tanh(golden_dir, cfg_kitti, o
     # and a whole run converges to a finite result
     r = opt.reconstruct_batch([dict(t_cam_obj=st["sdf_t_cam_obj"], pts=st["sdf_pts"], code=st["sdf_z"])])[0]
     assert r.is_good and np.isfinite(r.t_cam_obj).all()
+
+
+def test_inputs_built_on_the_device(dec_path, cfg_kitti):
+    """rays from pixel coordinates and the camera matrix inverse (loss_utils.get_rays,
+    reconstruct/loss_utils.py:23-37; src/LocalMapping_util.cc:378-386), world map points into the camera frame and the
+    object's world pose composed with the camera pose (LocalMapping_util.cc:344-352,390) -- all on the device, once per
+    upload.  The arrays the kernels then see equal the host-built ones to fp32 rounding, and the reconstruction equals
+    the one from host-built inputs."""
+    import ctypes as C
+    from dsp_slam_b200 import synth, _lib
+    FP = C.POINTER(C.c_float)
+    o = synth.make_object(123, 400, 300, 120)
+    K = np.array([[718.856, 0, 607.19], [0, 718.856, 185.2157], [0, 0, 1]], np.float64)          # KITTI-like intrinsics
+    invK = np.linalg.inv(K)
+    rays = np.asarray(o["rays"], np.float64)
+    pix = (rays @ K.T)[:, :2] / (rays @ K.T)[:, 2:3]                                              # the pixels those rays came from
+    # a camera pose in the world, the object and its points expressed in the world
+    a = 0.3
+    Twc = np.eye(4); Twc[:3, :3] = [[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]; Twc[:3, 3] = [2.0, -0.5, 7.0]
+    Tcw = np.linalg.inv(Twc)
+    pts_w = (np.asarray(o["pts"], np.float64) @ Twc[:3, :3].T + Twc[:3, 3]).astype(np.float32)
+    Two = (Twc @ np.asarray(o["t_cam_obj_init"], np.float64)).astype(np.float32)
+    opt = _engine_or_skip("tc", dec_path["cars"], cfg_kitti)
+    dev_obj = dict(t_cam_obj=Two, pts=np.asfortranarray(pts_w), pixels=np.asfortranarray(pix.astype(np.float32)),
+                   inv_k=invK.astype(np.float32), depth=o["depth"], t_cam_world=Tcw.astype(np.float32))
+    opt.solver.upload([dev_obj])
+    n, m = 400, 420
+    T = np.zeros((4, 4), np.float32); P = np.zeros((n, 3), np.float32); R = np.zeros((m, 3), np.float32)
+    _lib.check(_lib.load().dspgn_debug_inputs(opt.solver.handle, 0, T.ctypes.data_as(FP), P.ctypes.data_as(FP), R.ctypes.data_as(FP)))
+    # what the reference's host code computes (get_rays in float64 -> float32; Eigen / OpenCV products in float32)
+    rays_ref = (np.concatenate([pix.astype(np.float32).astype(np.float64), np.ones((m, 1))], 1)[:, None, :] * invK.astype(np.float32).astype(np.float64)).sum(-1)
+    np.testing.assert_allclose(R, rays_ref.astype(np.float32), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(R, np.asarray(o["rays"]), rtol=0, atol=2e-4)                       # and they are the original rays
+    pts_c = pts_w.astype(np.float64) @ Tcw[:3, :3].T + Tcw[:3, 3]
+    np.testing.assert_allclose(P, pts_c.astype(np.float32), rtol=0, atol=5e-6)
+    np.testing.assert_allclose(T, (Tcw @ Two.astype(np.float64)).astype(np.float32), rtol=0, atol=5e-6)
+    # reconstruction from device-built inputs == from the host-built ones (same arithmetic up to fp32 rounding of the inputs)
+    r_dev = opt.reconstruct_batch([dev_obj])[0]
+    r_host = opt.reconstruct_batch([dict(t_cam_obj=T.copy(), pts=P.copy(), rays=R.copy(), depth=o["depth"])])[0]
+    assert r_dev.is_good and r_host.is_good
+    np.testing.assert_array_equal(r_dev.t_cam_obj, r_host.t_cam_obj)         # identical device inputs -> identical bits
+    np.testing.assert_array_equal(r_dev.code, r_host.code)
