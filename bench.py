@@ -292,9 +292,13 @@ def run_ours(args):
             dist.all_reduce(t, op=op or dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local) if rank == 0 else None      # started before the warm-up: nvidia-smi takes ~0.2 s to deliver its first sample
     for _ in range(max(args.warmup, 3)):
         step()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 2.0:
+            time.sleep(0.02)
     ms_local, t0, t1 = timed_loop(step, args.steps)
     clocks = sampler.stop(t0, t1) if sampler else None
     launches_per_step = solver.counters()["kernel_launches"]

@@ -773,14 +773,27 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
               uint32_t v[32];
               tc_ld32(d_t + (uint32_t)n0, v);         // columns beyond n_mma are never used below
               tc_wait_ld();
+              if (L == kMaxCode && n0 + 32 <= kMaxCode) {
+                // thread-per-row accesses as float4: with the 76-float row stride a quarter-warp covers all 32 banks
+                // (the scalar form was a 4-way bank conflict)
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int ii = n0 + i;
-                if (ii < in0) {
-                  const int jc = (ii < L) ? ii : (kMaxCode + ii - L);
-                  float g = __uint_as_float(v[i]);
-                  if (has_skip) g += jr[jc];
-                  jr[jc] = g * sc;                                 // loss.py:145 (de_ds) / inactive rows
+                for (int i = 0; i < 32; i += 4) {
+                  float4* pj = reinterpret_cast<float4*>(jr + n0 + i);
+                  float4 g = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                  if (has_skip) { const float4 k = *pj; g.x += k.x; g.y += k.y; g.z += k.z; g.w += k.w; }
+                  g.x *= sc; g.y *= sc; g.z *= sc; g.w *= sc;      // loss.py:145 (de_ds) / inactive rows
+                  *pj = g;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const int ii = n0 + i;
+                  if (ii < in0) {
+                    const int jc = (ii < L) ? ii : (kMaxCode + ii - L);
+                    float g = __uint_as_float(v[i]);
+                    if (has_skip) g += jr[jc];
+                    jr[jc] = g * sc;                               // loss.py:145 (de_ds) / inactive rows
+                  }
                 }
               }
             }
