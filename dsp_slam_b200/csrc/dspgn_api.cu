@@ -602,7 +602,7 @@ int launch_init(DspgnSolver* s, int pose_only, bool mega = false, bool render = 
     ia.obj_iter = s->d_obj_iter.as<int>();
     ia.total_tiles0 = s->total_tiles128 + (render ? (int)s->total_ray_tiles128 : 0);
   }
-  k_init<<<s->n_obj, 256, 0, s->stream>>>(ia);
+  k_init<<<s->n_obj, 128, 0, s->stream>>>(ia);
   s->ctr.kernel_launches++;
   CU(cudaGetLastError());
   return 0;

@@ -170,15 +170,14 @@ struct InitArgs {
   const DecoderDev* decs;  // layer-0 fold (ObjState.zb0)
 };
 
-// zb0 = b0 + W0[:, :L] z   (fp32 FMA chain in i order; all threads of the calling CTA / epilogue).  zsh: the code in
-// shared memory (kMaxCode floats, filled and synchronised by the caller).
-__device__ __forceinline__ void refresh_zb0(ObjState& st, const DecoderDev& dec, int tid, int nthreads, const float* zsh) {
-  const float* __restrict__ W = dec.Wf[0];      // reduction-major [in][256]: consecutive threads read consecutive floats
+// zb0 = b0 + W0[:, :L] z   (fp32 FMA chain in i order; all threads of the calling CTA / epilogue)
+// (a variant with the code staged in shared memory and __ldg weight reads measured SLOWER: +9 us per solve, +12 us k_init)
+__device__ __forceinline__ void refresh_zb0(ObjState& st, const DecoderDev& dec, int tid, int nthreads) {
+  const float* __restrict__ W = dec.Wf[0];      // reduction-major [in][256]
   const float* __restrict__ b = dec.bias[0];
   for (int j = tid; j < kHid; j += nthreads) {
     float acc = b[j];
-#pragma unroll 8
-    for (int i = 0; i < dec.L; ++i) acc = fmaf(__ldg(W + i * kHid + j), zsh[i], acc);
+    for (int i = 0; i < dec.L; ++i) acc = fmaf(W[i * kHid + j], ldv(&st.z[i]), acc);
     st.zb0[j] = acc;
   }
 }
@@ -190,11 +189,7 @@ __global__ void k_init(InitArgs a) {
   const ObjMeta M = a.meta[o];
   if (a.pt_active != nullptr)
     for (int i = tid; i < M.n_pts; i += blockDim.x) a.pt_active[M.pts_off + i] = 1;
-  __shared__ float zsh[kMaxCode];
-  if (tid < kMaxCode) {
-    const float zv = (M.has_code && tid < a.code_len) ? a.code_init[o * kMaxCode + tid] : 0.f;
-    st.z[tid] = zv; zsh[tid] = zv;
-  }
+  if (tid < kMaxCode) st.z[tid] = (M.has_code && tid < a.code_len) ? a.code_init[o * kMaxCode + tid] : 0.f;
   if (tid == 0) {
     float Tco[12];
     for (int r = 0; r < 3; ++r)
@@ -209,7 +204,7 @@ __global__ void k_init(InitArgs a) {
     a.band_m[o] = 0;
   }
   __syncthreads();
-  refresh_zb0(st, a.decs[M.class_id], tid, blockDim.x, zsh);
+  refresh_zb0(st, a.decs[M.class_id], tid, blockDim.x);
   if (M.bad) {                               // rejected at upload: no tile, no solve -- its record is final now
     __syncthreads();
     if (tid == 0) write_record(a.results, a.gather, o, st, a.pose_only, M.scale);
@@ -543,14 +538,9 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
   }
   // ---- update (optimizer.py:186-192 / :72-74), clear accumulators, next depth range -----------
   const bool fail = (s_flag != 0);
-  float* const zsh = As;                     // the eliminated system is dead: its storage carries the updated code
-  if (tid < kMaxCode) {
-    float zv = ldv(&st.z[tid]);
-    if (!a.pose_only && tid < L && !fail) { zv += prm.lr * xs[tid + 7]; st.z[tid] = zv; }
-    zsh[tid] = zv;
-  }
+  if (!a.pose_only && tid < L && !fail) st.z[tid] = ldv(&st.z[tid]) + prm.lr * xs[tid + 7];
   solve_sync<MEGA>();                        // the result record below reads every z entry
-  if (!a.pose_only && !fail && !last_iter) refresh_zb0(st, a.decs[a.meta[o].class_id], tid, kSolveThreads, zsh);
+  if (!a.pose_only && !fail && !last_iter) refresh_zb0(st, a.decs[a.meta[o].class_id], tid, kSolveThreads);
   if (tid == 0) {
     st.loss = loss; st.V = V; st.m = m;
     a.V_count[o] = 0;

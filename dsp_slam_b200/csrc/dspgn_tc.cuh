@@ -838,22 +838,32 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         int bi = 0, rem = tid;
         while (rem >= 18 - bi) { rem -= 18 - bi; ++bi; }
         const int bj = bi + rem;
-        float h[4][4];
+        // Packed fp32 FMAs (fma.rn.f32x2 -> FFMA2, two FMAs per lane and instruction: the plain FFMA pipe issues one
+        // warp instruction per two cycles, which made this loop 8k cycles on the two scheduler partitions that hold two of
+        // the six warps).  h2[u][w] = (h[u][2w], h[u][2w+1]); every FMA is the same operation as in the scalar form.
+        unsigned long long h2[4][2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) h[u][v] = 0.f;
+        for (int u = 0; u < 4; ++u) { h2[u][0] = 0ull; h2[u][1] = 0ull; }
         const float* pa = S.Jp + 4 * bi;
         const float* pb = S.Jp + 4 * bj;
 #pragma unroll 4
         for (int p = 0; p < kTcRows; ++p) {
           const float4 A4 = *reinterpret_cast<const float4*>(pa + p * kJpStride);
-          const float4 B4 = *reinterpret_cast<const float4*>(pb + p * kJpStride);
-          const float av[4] = {A4.x, A4.y, A4.z, A4.w}, bv[4] = {B4.x, B4.y, B4.z, B4.w};
+          const ulonglong2 B2 = *reinterpret_cast<const ulonglong2*>(pb + p * kJpStride);     // (b0, b1), (b2, b3)
+          const float av[4] = {A4.x, A4.y, A4.z, A4.w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < 4; ++u) {
+            unsigned long long aa;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(av[u]));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(h2[u][0]) : "l"(aa), "l"(B2.x));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(h2[u][1]) : "l"(aa), "l"(B2.y));
+          }
+        }
+        float h[4][4];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) h[u][v] = fmaf(av[u], bv[v], h[u][v]);
+        for (int u = 0; u < 4; ++u) {
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(h[u][0]), "=f"(h[u][1]) : "l"(h2[u][0]));
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(h[u][2]), "=f"(h[u][3]) : "l"(h2[u][1]));
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
