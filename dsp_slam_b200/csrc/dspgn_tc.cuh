@@ -12,10 +12,20 @@
 //     with 1-D bulk copies (cp.async.bulk -> UBLKCP) signalling mbarriers;
 //   * every product is formed as  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  (3 fp16 MMAs, fp32 accumulate):
 //     ~2^-21 relative error per product, which keeps the Gauss-Newton iteration inside the fp32 noise
-//     floor of the reference (>= 15 mantissa bits needed; bf16/tf32 single pass is not).
+//     floor of the reference (>= 15 mantissa bits needed; bf16/tf32 single pass is not);
+//   * only the hidden width x width layers are GEMM steps (14 per fwd+bwd tile of the 8 x 256 decoder): layer 0, with
+//     its latent part folded into a per-object bias, is 3 FMAs per output while the first operand is built, and the
+//     final Linear(width, 1) + tanh is a per-row dot product in the epilogue of the last hidden layer;
+//   * J^T J / J^T r of the tile on the CUDA cores with packed fp32 FMAs (FFMA2), written as per-tile partials.
 //
 // Warp roles (320 threads): warps 0-3 / 4-7 = epilogue groups (thread = tile row; group g owns accumulator
-// columns [128g, 128g+128)), warp 8 = MMA issuer (one elected lane), warp 9 = weight producer.
+// columns [128g, 128g+128)), warp 8 = MMA issuer (one elected lane), warp 9 = weight producer and, in the persistent
+// kernels, the CTA's scheduler (pops the device work queue).
+//
+// Three schedules share this body (template SCHED): 0 = one launch per term and iteration (k_decoder_tc), 1 = persistent
+// kernel with SDF tiles only (k_gn_persistent), 2 = persistent kernel with the render term: ray-sample tiles, 64-ray scan
+// items, band tiles, SDF tiles (k_gn_persistent_render).  The CTA that completes an object's last outstanding tile runs
+// its solve (dspgn_solve.cuh) and queues the next iteration.
 //
 // Restates the same reference arithmetic as dspgn_simt.cuh (loss.py:22-43,143-150; loss_utils.py:51-103;
 // deep_sdf_decoder.py:75-110; optimizer.py:161-167).
