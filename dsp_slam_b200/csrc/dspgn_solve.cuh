@@ -290,6 +290,38 @@ __device__ __forceinline__ void solve_sync() {
   else __syncthreads();
 }
 
+// Pivots [k0, k1) of the register-resident Gauss-Jordan elimination, touching the first 4*NCH entries of the rotated
+// rows (all later entries are zero on entry and stay zero).  Called by threads 0..95; one named barrier per pivot.
+template <int NCH>
+__device__ __forceinline__ void gj_pivots(const int k0, const int k1, const int tid, float (&arow)[kPMax + 1], float& brow,
+                                          float& mydiag, int& bad_pivot, float4 (&bcast)[2][(kPMax + 1) / 4 + 1]) {
+  constexpr int NE = 4 * NCH;                      // entries 0 .. NE-1 are live (entry NE-1 is already zero)
+#pragma unroll 1
+  for (int k = k0; k < k1; ++k) {
+    float4* buf = bcast[k & 1];
+    if (tid == k) {
+#pragma unroll
+      for (int j = 0; j < NE; j += 4) buf[j >> 2] = make_float4(arow[j], arow[j + 1], arow[j + 2], arow[j + 3]);
+      buf[(kPMax + 1) / 4] = make_float4(brow, 0.f, 0.f, 0.f);
+      mydiag = arow[0];
+    }
+    elim_bar();
+    float pr[NE];
+#pragma unroll
+    for (int j = 0; j < NE; j += 4) {
+      const float4 v = buf[j >> 2];
+      pr[j] = v.x; pr[j + 1] = v.y; pr[j + 2] = v.z; pr[j + 3] = v.w;
+    }
+    const float pb = buf[(kPMax + 1) / 4].x;
+    const float piv = pr[0];
+    if (!(piv > 0.f) || !(piv < 3.0e38f)) bad_pivot = 1;        // every thread sees the same pivot
+    const float l = (tid == k) ? 0.f : __fdividef(arow[0], piv);        // MUFU.RCP path: 47 vs 112 cycles per pivot for __frcp_rn (tools/probes/solve_probe.cu)
+#pragma unroll
+    for (int j = 1; j < NE; ++j) arow[j - 1] = fmaf(-l, pr[j], arow[j]);
+    brow = fmaf(-l, pb, brow);
+  }
+}
+
 // One CTA (or the epilogue half of one) per object: fixed-order reduction of the tile partials (fp64), priors
 // and damping (optimizer.py:161-184), Gaussian elimination of the SPD 71x71 system with thread = row in
 // registers, back-substitution, Sim(3)/SE(3) update, next depth range, soft failures (optimizer.py:130-150).
@@ -501,30 +533,12 @@ __device__ int solve_object(const SolveArgs& a, const int o, const int tid, Solv
     float brow = As[row * kAsStride + kPMax];
     float mydiag = 1.f;
     int bad_pivot = 0;
-#pragma unroll 1
-    for (int k = 0; k < kPMax; ++k) {
-      float4* buf = bcast[k & 1];
-      if (tid == k) {
-#pragma unroll
-        for (int j = 0; j <= kPMax; j += 4) buf[j >> 2] = make_float4(arow[j], arow[j + 1], arow[j + 2], arow[j + 3]);
-        buf[(kPMax + 1) / 4] = make_float4(brow, 0.f, 0.f, 0.f);
-        mydiag = arow[0];
-      }
-      elim_bar();
-      float pr[kPMax + 1];
-#pragma unroll
-      for (int j = 0; j <= kPMax; j += 4) {
-        const float4 v = buf[j >> 2];
-        pr[j] = v.x; pr[j + 1] = v.y; pr[j + 2] = v.z; pr[j + 3] = v.w;
-      }
-      const float pb = buf[(kPMax + 1) / 4].x;
-      const float piv = pr[0];
-      if (!(piv > 0.f) || !(piv < 3.0e38f)) bad_pivot = 1;        // every thread sees the same pivot
-      const float l = (tid == k) ? 0.f : __fdividef(arow[0], piv);        // MUFU.RCP path: 47 vs 112 cycles per pivot for __frcp_rn (tools/probes/solve_probe.cu)
-#pragma unroll
-      for (int j = 1; j <= kPMax; ++j) arow[j - 1] = fmaf(-l, pr[j], arow[j]);
-      brow = fmaf(-l, pb, brow);
-    }
+    // After k rotations only entries 0 .. 70-k of a rotated row can be non-zero, so the pivots run in three tiers that
+    // broadcast / load / update only the first 72, 48 and 24 entries (whole loop bodies specialised at compile time --
+    // per-chunk branches inside one body measured slower than no skipping at all).
+    gj_pivots<18>(0, 24, tid, arow, brow, mydiag, bad_pivot, bcast);
+    gj_pivots<12>(24, 48, tid, arow, brow, mydiag, bad_pivot, bcast);
+    gj_pivots<6>(48, kPMax, tid, arow, brow, mydiag, bad_pivot, bcast);
     if (tid < kPMax) xs[tid] = brow / mydiag;
     if (bad_pivot && tid == 0) s_flag = 1;
   }

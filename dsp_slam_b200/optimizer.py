@@ -116,66 +116,71 @@ class BatchSolver:
     def _pack(self, objs):
         """Marshal a list of object dicts into a DspgnObjectIn array (pointers + element strides; no data is
         copied -- Fortran-ordered / strided float32 arrays are passed as they are).  Built as a numpy
-        structured array with the exact C layout (a per-field ctypes loop costs 2x more per call)."""
+        structured array with the exact C layout, filled column by column from plain Python lists (per-element
+        assignments into the record array and `ndarray.ctypes` cost several times more per call)."""
         n = len(objs)
-        rec = np.zeros(n, dtype=_OBJ_DT)
-        Ts = [_as32(o["t_cam_obj"]) for o in objs]
-        Ps = [_as32(o["pts"]) for o in objs]
-        for T, P in zip(Ts, Ps):
+        cols = {k: [0] * n for k in ("t_cam_obj", "t_rs", "t_cs", "pts", "n_pts", "pts_rs", "pts_cs", "rays", "n_rays",
+                                     "rays_rs", "rays_cs", "depth", "n_depth", "code", "class_id", "pixels", "pix_rs",
+                                     "pix_cs", "inv_k", "t_cam_world")}
+        scale = [1.0] * n
+        keep = []
+        code_len = self.cfg.code_len
+        c_T, c_Trs, c_Tcs = cols["t_cam_obj"], cols["t_rs"], cols["t_cs"]
+        c_P, c_nP, c_Prs, c_Pcs = cols["pts"], cols["n_pts"], cols["pts_rs"], cols["pts_cs"]
+        for i, o in enumerate(objs):
+            T = _as32(o["t_cam_obj"]); P = _as32(o["pts"])
             if T.shape != (4, 4) or P.ndim != 2 or P.shape[1] != 3:
                 raise ValueError("t_cam_obj must be (4,4) and pts (M,3)")
-        keep = [Ts, Ps]
-        rec["t_cam_obj"] = [a.ctypes.data for a in Ts]
-        st = np.array([a.strides for a in Ts], dtype=np.int64) >> 2
-        rec["t_rs"] = st[:, 0]; rec["t_cs"] = st[:, 1]
-        rec["pts"] = [a.ctypes.data for a in Ps]
-        sp = np.array([a.strides for a in Ps], dtype=np.int64) >> 2
-        rec["pts_rs"] = sp[:, 0]; rec["pts_cs"] = sp[:, 1]
-        rec["n_pts"] = [a.shape[0] for a in Ps]
-        rec["scale"] = 1.0
-        code_len = self.cfg.code_len
-        for i, o in enumerate(objs):                       # optional members
+            keep.append((T, P))
+            c_T[i] = T.__array_interface__["data"][0]; st = T.strides; c_Trs[i] = st[0] >> 2; c_Tcs[i] = st[1] >> 2
+            c_P[i] = P.__array_interface__["data"][0]; st = P.strides; c_Prs[i] = st[0] >> 2; c_Pcs[i] = st[1] >> 2
+            c_nP[i] = P.shape[0]
             px = o.get("pixels")
-            if px is not None and len(px):
+            has_px = px is not None and len(px) > 0
+            if has_px:
                 # rays built on the device: rays = inv_k [u, v, 1] (loss_utils.get_rays, reconstruct/loss_utils.py:23-37)
                 px = _as32(px)
                 Kinv = np.ascontiguousarray(o["inv_k"], dtype=np.float32).reshape(3, 3)
                 D = o.get("depth")
                 D = np.ascontiguousarray(D if D is not None else np.zeros(0), dtype=np.float32).reshape(-1)
-                rec["pixels"][i] = px.ctypes.data; rec["n_rays"][i] = px.shape[0]
-                rec["pix_rs"][i] = px.strides[0] >> 2; rec["pix_cs"][i] = px.strides[1] >> 2
-                rec["inv_k"][i] = Kinv.ctypes.data
-                rec["depth"][i] = D.ctypes.data; rec["n_depth"][i] = D.shape[0]
+                cols["pixels"][i] = px.__array_interface__["data"][0]; cols["n_rays"][i] = px.shape[0]
+                cols["pix_rs"][i] = px.strides[0] >> 2; cols["pix_cs"][i] = px.strides[1] >> 2
+                cols["inv_k"][i] = Kinv.__array_interface__["data"][0]
+                cols["depth"][i] = D.__array_interface__["data"][0] if D.shape[0] else 0; cols["n_depth"][i] = D.shape[0]
                 keep.append((px, Kinv, D))
             Tcw = o.get("t_cam_world")
             if Tcw is not None:
                 # pts are WORLD map points and t_cam_obj the object's WORLD pose (src/LocalMapping_util.cc:344-352,390)
                 Tcw = np.ascontiguousarray(Tcw, dtype=np.float32).reshape(4, 4)
-                rec["t_cam_world"][i] = Tcw.ctypes.data
+                cols["t_cam_world"][i] = Tcw.__array_interface__["data"][0]
                 keep.append(Tcw)
-            R = o.get("rays") if px is None or not len(px) else None
+            R = None if has_px else o.get("rays")
             if R is not None and len(R):
                 R = _as32(R)
                 D = o.get("depth")
                 D = np.ascontiguousarray(D if D is not None else np.zeros(0), dtype=np.float32).reshape(-1)
                 rs = R.strides
-                rec["rays"][i] = R.ctypes.data; rec["n_rays"][i] = R.shape[0]
-                rec["rays_rs"][i] = rs[0] >> 2; rec["rays_cs"][i] = rs[1] >> 2
-                rec["depth"][i] = D.ctypes.data; rec["n_depth"][i] = D.shape[0]
+                cols["rays"][i] = R.__array_interface__["data"][0]; cols["n_rays"][i] = R.shape[0]
+                cols["rays_rs"][i] = rs[0] >> 2; cols["rays_cs"][i] = rs[1] >> 2
+                cols["depth"][i] = D.__array_interface__["data"][0] if D.shape[0] else 0; cols["n_depth"][i] = D.shape[0]
                 keep.append((R, D))
             Cd = o.get("code")
             if Cd is not None:
                 Cd = np.ascontiguousarray(Cd, dtype=np.float32).reshape(-1)
                 if Cd.shape[0] < code_len:                 # zero-pad (optimizer.py:97-100 slices code[:code_len])
                     Cd = np.concatenate([Cd, np.zeros(code_len - Cd.shape[0], np.float32)])
-                rec["code"][i] = Cd.ctypes.data
+                cols["code"][i] = Cd.__array_interface__["data"][0]
                 keep.append(Cd)
             sc = o.get("scale")
             if sc is not None:
-                rec["scale"][i] = float(sc)
+                scale[i] = float(sc)
             cid = o.get("class_id")
             if cid:
-                rec["class_id"][i] = int(cid)
+                cols["class_id"][i] = int(cid)
+        rec = np.zeros(n, dtype=_OBJ_DT)
+        for k, v in cols.items():
+            rec[k] = v
+        rec["scale"] = scale
         keep.append(rec)
         return rec.ctypes.data_as(C.POINTER(_lib.ObjectIn)), keep
 
