@@ -215,6 +215,7 @@ struct TcSmemTail {
   // parameters themselves would make them address-taken: the compiler then parks all of them in local memory and the tile
   // loop reads its pointers with LDL instead of from the constant bank.
   MegaArgs ctx_q; SolveArgs ctx_sv; int ctx_D;
+  int push_base, push_nF, push_nS;        // cooperative publication of an object's next-iteration tiles
 };
 constexpr size_t kTcSmemBytes = 1024 + (size_t)kTcStages * kTcStageBytes + sizeof(TcSmemTail);
 
@@ -330,9 +331,12 @@ __device__ __noinline__ void mega_solve_and_advance(TcSmemTail& S, int o, int ti
   if (tid == 0) mega_event(q, EV_SOLVE_BEGIN, 0, o, it);
   const int fin = solve_object<true>(sv, o, tid, SM, it + 1 >= q.n_iters);
   epi_bar_sync();
+  // ---- publish: finished, or the tiles of the next iteration.  All 256 threads write the queue slots (one thread
+  // pushing 176 ray tiles + their flags one by one took ~3 us on the single-object critical path).
   if (tid == 0) {
     mega_event(q, EV_SOLVE_END, 0, o, it);
     __threadfence();                         // state / result record before anything is published
+    int base = -1;
     if (fin) {
       atomicAdd(q.done_objects, 1);
     } else {
@@ -343,9 +347,20 @@ __device__ __noinline__ void mega_solve_and_advance(TcSmemTail& S, int o, int ti
       *reinterpret_cast<volatile int*>(q.pending + o) = ntS + (ntF > 0 ? 1 : 0);
       *reinterpret_cast<volatile int*>(q.ray_left + o) = ntF;
       __threadfence();
-      mega_push(q, MODE_RAYFWD, o, ntF);      // the long chain (rays -> scan -> band -> solve) first
-      mega_push(q, MODE_SDF, o, ntS);
+      base = atomicAdd(q.q_tail, ntF + ntS);  // the long chain (rays -> scan -> band -> solve) first, then the SDF tiles
+      S.push_nF = ntF; S.push_nS = ntS;
     }
+    S.push_base = base;
+  }
+  epi_bar_sync();
+  const int base = S.push_base;
+  if (base >= 0) {
+    const int nF = S.push_nF, n = nF + S.push_nS;
+    for (int j = tid; j < n; j += kTcEpiThreads)
+      *reinterpret_cast<volatile int*>(q.q_items + base + j) = (j < nF) ? make_item(MODE_RAYFWD, o, j) : make_item(MODE_SDF, o, j - nF);
+    __threadfence();
+    epi_bar_sync();                           // every item is written (and fenced) before the first flag goes up
+    for (int j = tid; j < n; j += kTcEpiThreads) *reinterpret_cast<volatile int*>(q.q_flag + base + j) = 1;
   }
 }
 
