@@ -522,7 +522,7 @@ int upload_batch_impl(DspgnSolver* s, int n_obj, const DspgnObjectIn* in, bool d
   bad |= s->d_V.reserve(4 * (size_t)n_obj);
   bad |= s->d_m.reserve(4 * (size_t)n_obj);
   bad |= s->d_results.reserve(4 * DSPGN_RESULT_FLOATS * (size_t)n_obj);
-  bad |= s->h_results.reserve(4 * DSPGN_RESULT_FLOATS * (size_t)n_obj);
+  bad |= s->h_results.reserve(4 * DSPGN_RESULT_FLOATS * (size_t)n_obj + 512);
   const size_t smp = (size_t)(ts > 0 ? ts : 1);
   if (render) {
     bad |= s->d_sdf.reserve(4 * smp);
@@ -947,20 +947,18 @@ int dspgn_results(DspgnSolver* s, DspgnObjectOut* out) {
   CU(cudaSetDevice(s->device));
   static_assert(sizeof(DspgnObjectOut) == 4 * DSPGN_RESULT_FLOATS, "result record layout");
   const size_t bytes = sizeof(DspgnObjectOut) * (size_t)s->n_obj;
+  const bool mega = s->mega_ran;           // the queue counters (abort flag, band-row total) ride on the same copy + sync
+  if (s->h_results.reserve(bytes + 512)) return fail(DSPGN_E_ALLOC, "cudaMallocHost");
+  int* hq = reinterpret_cast<int*>(s->h_results.as<unsigned char>() + ((bytes + 63) / 64) * 64);
   CU(cudaMemcpyAsync(s->h_results.p, s->d_results.p, bytes, cudaMemcpyDeviceToHost, s->stream));
+  if (mega) CU(cudaMemcpyAsync(hq, s->d_q_ctr.as<int>() + 64, 4 * 40, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   memcpy(out, s->h_results.p, bytes);
-  if (s->mega_ran) {
-    int aborted = 0;
-    if (cudaMemcpy(&aborted, s->d_q_ctr.as<int>() + 96, 4, cudaMemcpyDeviceToHost) != cudaSuccess) cudaGetLastError();
+  if (mega) {
     s->mega_ran = false;
-    if (aborted) return fail(DSPGN_E_CUDA, "persistent kernel: a work-queue wait timed out (aborted softly; results incomplete)");
-  }
-  if (s->band_rows_pending) {          // band rows the persistent kernel processed (data dependent): roofline accounting
-    int m_total = 0;
-    if (cudaMemcpy(&m_total, s->d_q_ctr.as<int>() + 80, 4, cudaMemcpyDeviceToHost) == cudaSuccess) s->ctr.rows_fwd_bwd += m_total;
-    else cudaGetLastError();
+    if (s->band_rows_pending) s->ctr.rows_fwd_bwd += hq[80 - 64];   // band rows the persistent kernel processed (roofline accounting)
     s->band_rows_pending = false;
+    if (hq[96 - 64]) return fail(DSPGN_E_CUDA, "persistent kernel: a work-queue wait timed out (aborted softly; results incomplete)");
   }
   if (s->timing) {
     float dec = 0.f;

@@ -87,6 +87,20 @@ def _objectin_dtype():
 
 _OBJ_DT = _objectin_dtype()
 
+_fastpack = False          # False = not tried yet, None = unavailable
+
+
+def _fastpack_mod():
+    """The optional CPython extension that fills DspgnObjectIn records natively (csrc/fastpack.c)."""
+    global _fastpack
+    if _fastpack is False:
+        try:
+            from . import _fastpack as m
+            _fastpack = m
+        except ImportError:
+            _fastpack = None
+    return _fastpack
+
 
 class BatchSolver:
     """Thin object wrapper over a DspgnSolver handle (one GPU)."""
@@ -119,6 +133,11 @@ class BatchSolver:
         structured array with the exact C layout, filled column by column from plain Python lists (per-element
         assignments into the record array and `ndarray.ctypes` cost several times more per call)."""
         n = len(objs)
+        fp = _fastpack_mod()
+        if fp is not None and type(objs) is list:
+            rec = np.zeros(n, dtype=_OBJ_DT)
+            if fp.pack(objs, int(self.cfg.code_len), rec.ctypes.data):       # plain float32 numpy inputs: no Python per field
+                return rec.ctypes.data_as(C.POINTER(_lib.ObjectIn)), [rec, objs]
         cols = {k: [0] * n for k in ("t_cam_obj", "t_rs", "t_cs", "pts", "n_pts", "pts_rs", "pts_cs", "rays", "n_rays",
                                      "rays_rs", "rays_cs", "depth", "n_depth", "code", "class_id", "pixels", "pix_rs",
                                      "pix_cs", "inv_k", "t_cam_world")}

@@ -245,3 +245,39 @@ def test_drop_in_shim_module_next_to_the_reference_package():
     del bad["optimizer"]["joint_optim"]["k3"]
     with pytest.raises(KeyError):
         mod.Optimizer(object(), bad)
+
+
+def test_native_packer_equals_python_packer():
+    """csrc/fastpack.c (CPython extension) fills the DspgnObjectIn records for plain float32 numpy inputs; anything else
+    falls back to the Python path.  Both must produce byte-identical records."""
+    import ctypes as C
+    from dsp_slam_b200 import optimizer as O, synth, _lib
+    if O._fastpack_mod() is None:
+        pytest.skip("_fastpack extension not built")
+    bs = O.BatchSolver.__new__(O.BatchSolver)
+    bs.cfg = _lib.Config(); bs.cfg.code_len = 64
+    objs = synth.make_batch(5, 300, 120, 40, cls=["cars", "chairs", "cars", "chairs", "cars"], init_code_frac=0.5)
+    ins = []
+    for i, o in enumerate(objs):
+        d = dict(t_cam_obj=o["t_cam_obj_init"], pts=o["pts"], rays=o["rays"], depth=o["depth"], code=o["code_init"], class_id=i & 1)
+        ins.append(d)
+    ins[1] = dict(ins[1], pts=np.ascontiguousarray(ins[1]["pts"]), scale=1.7)                 # C-ordered, with a scale
+    ins[2] = dict(t_cam_obj=ins[2]["t_cam_obj"], pts=ins[2]["pts"])                            # no rays, no code
+    ins[3] = dict(t_cam_obj=ins[3]["t_cam_obj"], pts=ins[3]["pts"], pixels=np.asfortranarray(np.random.default_rng(0).random((50, 2), np.float32)),
+                  inv_k=np.eye(3, dtype=np.float32), depth=np.zeros(10, np.float32), t_cam_world=np.eye(4, dtype=np.float32))
+
+    def records(use_native):
+        O._fastpack = False if use_native else None
+        arr, keep = bs._pack(ins)
+        return [bytes(C.string_at(C.addressof(arr[i]), C.sizeof(_lib.ObjectIn))) for i in range(len(ins))], keep
+    try:
+        fast, keep_f = records(True)
+        slow, keep_s = records(False)
+    finally:
+        O._fastpack = False
+    assert len(keep_f) == 2 and keep_f[1] is ins               # the native path keeps the record array and the caller's list
+    assert fast == slow
+    # float64 / list inputs: the native path declines, the Python path converts
+    mixed = [dict(t_cam_obj=np.eye(4).tolist(), pts=np.zeros((5, 3)))]
+    arr, keep = bs._pack(mixed)
+    assert arr[0].n_pts == 5 and isinstance(keep[0], tuple) and keep[0][1].dtype == np.float32    # converted copies are kept alive
