@@ -95,6 +95,9 @@ def _fastpack_mod():
     global _fastpack
     if _fastpack is False:
         try:
+            import os
+            if os.environ.get("DSPGN_NO_FASTPACK"):
+                raise ImportError("disabled by DSPGN_NO_FASTPACK")
             from . import _fastpack as m
             _fastpack = m
         except ImportError:
