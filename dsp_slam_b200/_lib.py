@@ -11,6 +11,7 @@ MAX_LINEAR = 12
 RESULT_FLOATS = 88
 
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
+SCHED_AUTO, SCHED_LAUNCHES, SCHED_PERSISTENT = 0, 1, 2
 ST_OK, ST_SDF_NAN, ST_RENDER_FEW, ST_RENDER_NAN, ST_SOLVE, ST_BAD_INPUT = 0, 1, 2, 3, 4, 5
 E_ARG, E_CUDA, E_NOGPU, E_ALLOC, E_PEER = -1, -2, -3, -4, -5
 IPC_HANDLE_BYTES = 64
@@ -32,7 +33,8 @@ class Config(C.Structure):
                 ("b1", C.c_float), ("b2", C.c_float), ("lr", C.c_float), ("s_damp", C.c_float),
                 ("num_iterations", C.c_int32), ("code_len", C.c_int32),
                 ("num_depth_samples", C.c_int32), ("cut_off", C.c_float),
-                ("pose_only_iterations", C.c_int32), ("sdf_only", C.c_int32), ("engine", C.c_int32)]
+                ("pose_only_iterations", C.c_int32), ("sdf_only", C.c_int32), ("engine", C.c_int32),
+                ("schedule", C.c_int32)]
 
 
 _FP = C.POINTER(C.c_float)

@@ -317,6 +317,9 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
     }
   if (int rc = tc_setup_kernels(g_err)) { dspgn_solver_destroy(s); return rc; }
   if (const char* m = getenv("DSPGN_MEGA")) s->mega_enabled = (m[0] != '0');
+  if (cfg->schedule == DSPGN_SCHED_LAUNCHES) s->mega_enabled = false;
+  else if (cfg->schedule == DSPGN_SCHED_PERSISTENT) s->mega_enabled = true;
+  else if (cfg->schedule != DSPGN_SCHED_AUTO) { dspgn_solver_destroy(s); return fail(DSPGN_E_ARG, "bad schedule"); }
   if (getenv("DSPGN_CLK")) {
     const size_t nb = sizeof(long long) * (kClkTiles * kTcMaxSteps * kClkSlots + 16);
     if (s->d_clk.reserve(nb)) { dspgn_solver_destroy(s); return fail(DSPGN_E_ALLOC, "cudaMalloc"); }

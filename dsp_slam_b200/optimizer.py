@@ -299,7 +299,7 @@ def _unpack_all(out, n, code_len):
 class Optimizer(object):
     """Drop-in for reconstruct.optimizer.Optimizer (reconstruct/optimizer.py:26-203)."""
 
-    def __init__(self, decoder, configs, device=0, engine=None, sdf_only=False, extra_decoders=()):
+    def __init__(self, decoder, configs, device=0, engine=None, sdf_only=False, extra_decoders=(), schedule=None):
         optim_cfg = _cfg_get(configs, "optimizer")
         joint = _cfg_get(optim_cfg, "joint_optim")
         # exactly the keys optimizer.py:27-43 reads; a missing key raises KeyError like the reference
@@ -332,6 +332,9 @@ class Optimizer(object):
         c.sdf_only = int(bool(sdf_only))
         c.engine = {None: _lib.ENGINE_AUTO, "auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT,
                     "tc": _lib.ENGINE_TC}[engine]
+        # kernel schedule (bit-identical results): None/"auto", "launches" (one launch per term per iteration), "persistent"
+        c.schedule = {None: _lib.SCHED_AUTO, "auto": _lib.SCHED_AUTO, "launches": _lib.SCHED_LAUNCHES,
+                      "persistent": _lib.SCHED_PERSISTENT}[schedule]
         self.solver = BatchSolver(self._dev_decoders, c, device)
 
     # -- reference surface --------------------------------------------------------------------

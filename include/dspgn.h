@@ -53,6 +53,11 @@ extern "C" {
 #define DSPGN_ST_SOLVE 4       /* normal matrix not positive definite / non-finite step */
 #define DSPGN_ST_BAD_INPUT 5   /* unusable detection (no surface points, too many rays, ...): never evaluated */
 
+/* kernel schedules of a run (results are bit-identical; the per-iteration schedule exists for debugging / profiling) */
+#define DSPGN_SCHED_AUTO 0
+#define DSPGN_SCHED_LAUNCHES 1   /* one launch per residual term and solve per GN iteration */
+#define DSPGN_SCHED_PERSISTENT 2 /* one persistent object-pipelined kernel for all iterations (tensor-core engine only) */
+
 /* decoder engines */
 #define DSPGN_ENGINE_AUTO 0
 #define DSPGN_ENGINE_SIMT 1    /* fp32 FFMA kernels: on-device ground truth */
@@ -99,6 +104,7 @@ typedef struct {
   int32_t pose_only_iterations;/* pose_only_optim.num_iterations */
   int32_t sdf_only;            /* 1: skip the render term (BASELINE config 2 "surface-SDF loss") */
   int32_t engine;              /* DSPGN_ENGINE_* */
+  int32_t schedule;            /* DSPGN_SCHED_*: 0 = automatic (persistent kernel on the tensor-core engine) */
 } DspgnConfig;
 
 /* One detection, host side.  Strides are in elements (floats). */

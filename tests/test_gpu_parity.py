@@ -314,14 +314,9 @@ def test_mixed_classes_through_persistent_kernel(dec_path, cfg_kitti, oracle, or
         assert np.abs(r.t_cam_obj - ref["t_cam_obj"]).max() < (3e-3 if m >= 500 else 2e-2)
         assert np.abs(r.code - ref["code"]).max() < (1e-3 if m >= 500 else 8e-3)
     # the persistent schedule and the per-iteration schedule are bit-identical
-    import os
-    os.environ["DSPGN_MEGA"] = "0"
-    try:
-        opt2 = _engine_or_skip("tc", dec_path["cars"], cfg_kitti, sdf_only=True, extra_decoders=[dec_path["chairs"]])
-        rs2 = opt2.reconstruct_batch([dict(t_cam_obj=o["t_cam_obj_init"], pts=o["pts"], class_id=(0 if c == "cars" else 1))
-                                      for o, c in zip(objs, clss)])
-    finally:
-        os.environ.pop("DSPGN_MEGA", None)
+    opt2 = _engine_or_skip("tc", dec_path["cars"], cfg_kitti, sdf_only=True, extra_decoders=[dec_path["chairs"]], schedule="launches")
+    rs2 = opt2.reconstruct_batch([dict(t_cam_obj=o["t_cam_obj_init"], pts=o["pts"], class_id=(0 if c == "cars" else 1))
+                                  for o, c in zip(objs, clss)])
     for a_, b_ in zip(rs, rs2):
         np.testing.assert_array_equal(a_.t_cam_obj, b_.t_cam_obj)
         np.testing.assert_array_equal(a_.code, b_.code)
@@ -614,11 +609,7 @@ def test_render_term_through_persistent_kernel(dec_path, cfg_kitti, oracle, orac
     assert c1["kernel_launches"] <= 3, c1
     assert [r.is_good for r in rs] == [True, True, True, True, True, False, False, True]
     assert rs[5].status == 2 and rs[6].status == 2
-    os.environ["DSPGN_MEGA"] = "0"
-    try:
-        opt2 = _engine_or_skip("tc", dec_path["cars"], cfg, extra_decoders=[dec_path["chairs"]])
-    finally:
-        os.environ.pop("DSPGN_MEGA", None)
+    opt2 = _engine_or_skip("tc", dec_path["cars"], cfg, extra_decoders=[dec_path["chairs"]], schedule="launches")
     rs2 = opt2.reconstruct_batch(ins)
     assert opt2.solver.counters()["kernel_launches"] > 20
     for a_, b_ in zip(rs, rs2):
