@@ -76,8 +76,8 @@ def records_to_results(rec, code_len):
     status = ints[:, 81].tolist()
     loss = rec[:, 80].tolist()
     nv, nb = ints[:, 82].tolist(), ints[:, 83].tolist()
-    T = rec[:, :16].reshape(-1, 4, 4)
-    Z = rec[:, 16:16 + code_len]
+    T = list(rec[:, :16].reshape(-1, 4, 4))         # row views created in one go (cheaper than indexing per object)
+    Z = list(rec[:, 16:16 + code_len])
     out = []
     for i, st in enumerate(status):
         if st != 0:
