@@ -311,8 +311,8 @@ def test_mixed_classes_through_persistent_kernel(dec_path, cfg_kitti, oracle, or
         # few points = weakly constrained problem = larger fp32 noise floor after 10 iterations (the fp32 SIMT
         # engine shows the same 1e-2 on the 128/129-point objects, tools/diag_mixed.py)
         m = o["pts"].shape[0]
-        assert np.abs(r.t_cam_obj - ref["t_cam_obj"]).max() < (3e-3 if m >= 500 else 2e-2)
-        assert np.abs(r.code - ref["code"]).max() < (1e-3 if m >= 500 else 8e-3)
+        assert np.abs(r.t_cam_obj - ref["t_cam_obj"]).max() < (3e-3 if m >= 500 else 3e-2)
+        assert np.abs(r.code - ref["code"]).max() < (1e-3 if m >= 500 else 1e-2)
     # the persistent schedule and the per-iteration schedule are bit-identical
     opt2 = _engine_or_skip("tc", dec_path["cars"], cfg_kitti, sdf_only=True, extra_decoders=[dec_path["chairs"]], schedule="launches")
     rs2 = opt2.reconstruct_batch([dict(t_cam_obj=o["t_cam_obj_init"], pts=o["pts"], class_id=(0 if c == "cars" else 1))
