@@ -103,7 +103,8 @@ struct DspgnSolver {
   long long total_ray_tiles128 = 0;// ray-sample tiles of the batch
   int max_tiles128 = 0;            // largest tile count of one term of one object (queue items hold 19 bits)
   bool mega_enabled = true;
-  DevBuf d_clk, d_ev, d_seg, d_ln;
+  bool compact_rays = true;        // persistent kernel, render term: forward-only tiles over the valid-sample hulls only (env DSPGN_COMPACT_RAYS=0: all n_rays x D samples)
+  DevBuf d_clk, d_ev, d_seg, d_ln, d_vpre;
   bool clk_on = false;
   HostBuf h_results;
   // counters
@@ -317,6 +318,7 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
     }
   if (int rc = tc_setup_kernels(g_err)) { dspgn_solver_destroy(s); return rc; }
   if (const char* m = getenv("DSPGN_MEGA")) s->mega_enabled = (m[0] != '0');
+  if (const char* m = getenv("DSPGN_COMPACT_RAYS")) s->compact_rays = (m[0] != '0');   // A/B switch of the valid-sample hulls
   if (cfg->schedule == DSPGN_SCHED_LAUNCHES) s->mega_enabled = false;
   else if (cfg->schedule == DSPGN_SCHED_PERSISTENT) s->mega_enabled = true;
   else if (cfg->schedule != DSPGN_SCHED_AUTO) { dspgn_solver_destroy(s); return fail(DSPGN_E_ARG, "bad schedule"); }
@@ -350,7 +352,7 @@ void dspgn_solver_destroy(DspgnSolver* s) {
   dspgn_gather_close(s);
   for (DevBuf* b : {&s->d_decs, &s->d_stage, &s->d_state, &s->d_part_s, &s->d_part_r, &s->d_tbase, &s->d_V, &s->d_m, &s->d_results, &s->d_active,
                     &s->d_sdf, &s->d_bx, &s->d_bs, &s->d_br, &s->d_dbg, &s->d_clk, &s->d_q_items, &s->d_q_flag, &s->d_q_ctr,
-                    &s->d_tiles_left, &s->d_obj_iter, &s->d_ev, &s->d_seg, &s->d_ln}) b->release();
+                    &s->d_tiles_left, &s->d_obj_iter, &s->d_ev, &s->d_seg, &s->d_ln, &s->d_vpre}) b->release();
   s->h_stage.release();
   s->h_results.release();
   for (auto e : s->ev) cudaEventDestroy(e);
@@ -604,6 +606,8 @@ int launch_init(DspgnSolver* s, int pose_only, bool mega = false, bool render = 
     ia.pending = s->d_tiles_left.as<int>(); ia.ray_left = s->d_tiles_left.as<int>() + s->n_obj;
     ia.obj_iter = s->d_obj_iter.as<int>();
     ia.total_tiles0 = s->total_tiles128 + (render ? (int)s->total_ray_tiles128 : 0);
+    ia.rays = s->d_rays; ia.vpre = (render && s->compact_rays) ? s->d_vpre.as<int>() : nullptr;
+    ia.valid_rows_total = reinterpret_cast<unsigned long long*>(s->d_q_ctr.as<int>() + 88);
   }
   k_init<<<s->n_obj, 128, 0, s->stream>>>(ia);
   s->ctr.kernel_launches++;
@@ -714,6 +718,7 @@ int run_batch_impl(DspgnSolver* s, int mode) {
     bad |= s->d_tiles_left.reserve(4 * 3 * (size_t)s->n_obj);
     const size_t nseg_cap = (size_t)s->tot_rays / kSegRays + 2 * (size_t)s->n_obj + 4;
     if (render) bad |= s->d_seg.reserve(4 * 2 * nseg_cap);
+    if (render && s->compact_rays) bad |= s->d_vpre.reserve(4 * ((size_t)s->tot_rays + (size_t)s->n_obj + 4));
     bad |= s->d_obj_iter.reserve(4 * (size_t)s->n_obj);
     if (bad) return fail(DSPGN_E_ALLOC, "queue allocation failed");
     CU(cudaMemsetAsync(s->d_q_flag.p, 0, 4 * (size_t)cap, s->stream));
@@ -735,6 +740,8 @@ int run_batch_impl(DspgnSolver* s, int mode) {
     q.pending = s->d_tiles_left.as<int>(); q.ray_left = s->d_tiles_left.as<int>() + s->n_obj; q.obj_iter = s->d_obj_iter.as<int>();
     q.scan_left = s->d_tiles_left.as<int>() + 2 * s->n_obj;
     q.seg_cnt = s->d_seg.as<int>(); q.seg_prefix = s->d_seg.as<int>() + nseg_cap;
+    q.valid_rows_total = reinterpret_cast<unsigned long long*>(s->d_q_ctr.as<int>() + 88);
+    q.vpre = (render && s->compact_rays) ? s->d_vpre.as<int>() : nullptr;
     if (s->clk_on) {
       if (s->d_ev.reserve(8 * (1 + 2 * (size_t)kEvCap))) return fail(DSPGN_E_ALLOC, "cudaMalloc");
       CU(cudaMemsetAsync(s->d_ev.p, 0, 8, s->stream));
@@ -744,14 +751,14 @@ int run_batch_impl(DspgnSolver* s, int mode) {
     v.ev = q.ev; v.ev_cap = q.ev_cap;
     v.base_s = s->d_tbase_static; v.base_r = s->d_tbase_r_static; v.tile_rows = kTcRows; v.last_iter = 0; v.iter_index = 0; v.dbg_clk = nullptr;
     ScanArgs sa = base_scan(s);
+    sa.vpre = q.vpre;
     if (s->timing) cudaEventRecord(next_event(s), s->stream);
     if (render) k_gn_persistent_render<<<s->num_sms, kTcThreads, kTcSmemBytes, s->stream>>>(a, q, v, sa);
     else k_gn_persistent<<<s->num_sms, kTcThreads, kTcSmemBytes, s->stream>>>(a, q, v);
     if (s->timing) cudaEventRecord(next_event(s), s->stream);
     s->ctr.kernel_launches += 1;
     s->ctr.rows_fwd_bwd += (long long)s->tot_pts * iters;
-    if (render) s->ctr.rows_fwd_only += s->tot_smp * iters;
-    s->band_rows_pending = render;
+    s->band_rows_pending = render;           // band rows and valid ray samples are counted by the kernel (dspgn_results)
     s->mega_ran = true;
     CU(cudaGetLastError());
     CU(cudaEventRecord(s->ev_run1, s->stream));
@@ -959,7 +966,10 @@ int dspgn_results(DspgnSolver* s, DspgnObjectOut* out) {
   memcpy(out, s->h_results.p, bytes);
   if (mega) {
     s->mega_ran = false;
-    if (s->band_rows_pending) s->ctr.rows_fwd_bwd += hq[80 - 64];   // band rows the persistent kernel processed (roofline accounting)
+    if (s->band_rows_pending) {              // roofline accounting: what the reference decodes (loss.py:77-78, :143-144)
+      s->ctr.rows_fwd_bwd += hq[80 - 64];    // band rows of all iterations
+      { long long v; memcpy(&v, hq + (88 - 64), 8); s->ctr.rows_fwd_only += v; }   // V: ray samples inside the unit sphere, all iterations
+    }
     s->band_rows_pending = false;
     if (hq[96 - 64]) return fail(DSPGN_E_CUDA, "persistent kernel: a work-queue wait timed out (aborted softly; results incomplete)");
   }

@@ -103,6 +103,13 @@ __device__ __forceinline__ void xform_point(const float* __restrict__ T, float p
   oz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, T[8]), __fmul_rn(py, T[9])), __fmul_rn(pz, T[10])), T[11]);
 }
 
+// loss.py:68: a ray sample takes part in the render term when it lies inside the unit sphere.  ONE definition with
+// explicit roundings: the tile prologues of both engines and the valid-range pre-pass of the persistent kernel
+// (dspgn_solve.cuh: valid_sample_ranges) must take the same decision for the same sample.
+__device__ __forceinline__ bool inside_unit_sphere(float x, float y, float z) {
+  return sqrtf(__fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)))) < 1.0f;
+}
+
 // 3x4 [A|t] -> inverse [A^-1 | -A^-1 t] (adjugate, fp64 inside, fp32 out)
 __device__ inline void inv_affine(const float* T, float* out, double* det_out) {
   double a = T[0], b = T[1], c = T[2], d = T[4], e = T[5], f = T[6], g = T[8], h = T[9], i = T[10];

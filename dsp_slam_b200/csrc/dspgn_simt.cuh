@@ -73,6 +73,9 @@ constexpr int kKindScan = 3;   // queue-only kind: per-ray scan of a 64-ray chun
 __host__ __device__ __forceinline__ int make_item(int kind, int o, int tile) {
   return (kind << kItemKindShift) | (o << kItemObjShift) | tile;
 }
+// filler for reserved queue slots that turned out not to be needed (k_init reserves every object's iteration-0 slots
+// from host-side upper bounds): consumers skip it.  Never a real item: a scan item's tile index is < 128.
+constexpr int kItemNop = 0x7fffffff;
 struct MegaArgs {
   int n_iters;               // GN iterations per object
   int q_cap;                 // total items that can ever be pushed
@@ -87,6 +90,10 @@ struct MegaArgs {
   int* obj_iter;             // [n_obj] current iteration of each object
   int* done_objects;         // objects finished (last iteration or frozen)
   int* band_rows_total;      // sum of band rows over all objects and iterations (roofline accounting)
+  unsigned long long* valid_rows_total;   // sum of V (ray samples inside the unit sphere) over all objects and iterations
+  int* vpre;                 // per ray: (exclusive prefix of the valid-sample hulls << 7) | first valid sample, n_rays + 1
+                             // entries per object at ray_off + o (dspgn_solve.cuh: valid_sample_ranges); nullptr = the
+                             // forward-only tiles enumerate all n_rays * D samples
   int* abort_flag;           // set when a queue wait timed out: every CTA drains and exits (soft failure, never a trap)
   long long* ev; int ev_cap; // optional event log (env DSPGN_CLK): ev[0] = count, then {globaltimer ns, kind<<48|sm<<32|o<<20|tile}
 };
@@ -273,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decoder_simt(TermArgs a) {
           const float* q = a.rays + 3 * (size_t)(M.ray_off + ray);
           const float d = lin_depth(st.dmin, st.dmax, st.dstep, j, a.D);
           xform_point(st.T_oc, __fmul_rn(q[0], d), __fmul_rn(q[1], d), __fmul_rn(q[2], d), x, y, z);
-          sc = (sqrtf(x * x + y * y + z * z) < 1.0f) ? 1.f : 0.f;       // loss.py:68
+          sc = inside_unit_sphere(x, y, z) ? 1.f : 0.f;                // loss.py:68
         }
       }
       S.xo[p] = x; S.xo[kTP + p] = y; S.xo[2 * kTP + p] = z;

@@ -152,6 +152,61 @@ __global__ void k_build_inputs(BuildArgs a) {
   }
 }
 
+// ---- valid-sample ranges of the rays (persistent kernel with the render term) ------------------------------------------
+// loss.py:68 keeps the ray samples inside the unit sphere (the reference decodes only those V samples, loss.py:77-78).
+// Along a ray they are one run of consecutive samples (a line meets a ball in a segment) -- 70 % of the n_rays * D samples
+// on the real SLAM shape, 80-93 % on the BASELINE configs -- so the forward-only tiles of the persistent kernel enumerate
+// only the hull [first valid, last valid] of every ray:
+//   vpre[ray] = (exclusive prefix of the hull lengths << 7) | first valid sample,   vpre[n_rays] = total << 7.
+// Sample positions and the inside test are the tile prologue's own (lin_depth, xform_point, inside_unit_sphere), so a hull
+// contains exactly the samples the full enumeration marks valid; the prologue still tests every row it is given.
+// Called by all `nthreads` (multiple of 32, <= 1024) threads; s_wsum: 32 ints of shared memory.  Returns the total.
+__device__ __forceinline__ int vpre_base(const ObjMeta& M, int o) { return M.ray_off + o; }
+template <bool NAMED_BAR>
+__device__ __forceinline__ void vpre_sync() {
+  if (NAMED_BAR) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else __syncthreads();
+}
+template <bool NAMED_BAR>
+__device__ inline int valid_sample_ranges(const ObjMeta& M, const ObjState& st, const float* __restrict__ rays, const int D,
+                                          int* vp, const int tid, const int nthreads, int* s_wsum) {
+  const int lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
+  float T[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) T[i] = ldv(&st.T_oc[i]);
+  const float dmin = ldv(&st.dmin), dmax = ldv(&st.dmax), dstep = ldv(&st.dstep);
+  int carry = 0;
+  for (int r0 = 0; r0 < M.n_rays; r0 += nthreads) {
+    const int ray = r0 + tid;
+    int first = 0, cnt = 0;
+    if (ray < M.n_rays) {
+      const float* q = rays + 3 * (size_t)(M.ray_off + ray);
+      const float q0 = q[0], q1 = q[1], q2 = q[2];
+      int lo = -1, hi = -1;
+#pragma unroll 5
+      for (int j = 0; j < D; ++j) {             // independent samples: unrolled for instruction-level parallelism
+        const float d = lin_depth(dmin, dmax, dstep, j, D);
+        float x, y, z;
+        xform_point(T, __fmul_rn(q0, d), __fmul_rn(q1, d), __fmul_rn(q2, d), x, y, z);
+        if (inside_unit_sphere(x, y, z)) { if (lo < 0) lo = j; hi = j; }
+      }
+      if (lo >= 0) { first = lo; cnt = hi - lo + 1; }
+    }
+    int x = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) s_wsum[warp] = x;
+    vpre_sync<NAMED_BAR>();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) { const int v = s_wsum[w]; if (w < warp) woff += v; tot += v; }
+    if (ray < M.n_rays) vp[ray] = ((carry + woff + x - cnt) << 7) | first;
+    carry += tot;
+    vpre_sync<NAMED_BAR>();
+  }
+  if (tid == 0) vp[M.n_rays] = carry << 7;
+  return carry;
+}
+
 struct InitArgs {
   const ObjMeta* meta;
   ObjState* state;
@@ -168,6 +223,8 @@ struct InitArgs {
   float* results;          // records of objects rejected at upload are written here
   int n_bad;
   const DecoderDev* decs;  // layer-0 fold (ObjState.zb0)
+  unsigned long long* valid_rows_total;
+  const float* rays; int* vpre;   // render runs of the persistent kernel: valid-sample ranges (nullptr = off)
 };
 
 // zb0 = b0 + W0[:, :L] z   (fp32 FMA chain in i order; all threads of the calling CTA / epilogue)
@@ -211,12 +268,21 @@ __global__ void k_init(InitArgs a) {
   }
   if (a.mega) {
     const int ntS = (M.n_pts + a.tile_rows - 1) / a.tile_rows;
-    const int ntF = (a.render && !M.bad) ? (M.n_rays * a.D + a.tile_rows - 1) / a.tile_rows : 0;
+    // slots reserved by the host for this object's iteration 0: every ray sample + every SDF tile
+    const int ntF_cap = (a.render && !M.bad) ? (M.n_rays * a.D + a.tile_rows - 1) / a.tile_rows : 0;
+    int ntF = ntF_cap;
+    if (a.vpre != nullptr && ntF_cap > 0) {
+      __shared__ int s_wsum[32];
+      __syncthreads();                         // T_oc / depth range written by thread 0 above
+      const int vh = valid_sample_ranges<false>(M, st, a.rays, a.D, a.vpre + vpre_base(M, o), tid, blockDim.x, s_wsum);
+      ntF = (vh + a.tile_rows - 1) / a.tile_rows;
+    }
     const int base = a.q0_off[o];
     for (int j = tid; j < ntF; j += blockDim.x) { a.q_items[base + j] = make_item(MODE_RAYFWD, o, j); a.q_flag[base + j] = 1; }
     for (int j = tid; j < ntS; j += blockDim.x) { a.q_items[base + ntF + j] = make_item(MODE_SDF, o, j); a.q_flag[base + ntF + j] = 1; }
+    for (int j = ntF + ntS + tid; j < ntF_cap + ntS; j += blockDim.x) { a.q_items[base + j] = kItemNop; a.q_flag[base + j] = 1; }
     if (tid == 0) { a.pending[o] = ntS + (ntF > 0 ? 1 : 0); a.ray_left[o] = ntF; a.obj_iter[o] = 0; }
-    if (o == 0 && tid == 0) { *a.q_head = 0; *a.q_tail = a.total_tiles0; *a.done_objects = a.n_bad; *a.band_rows_total = 0; *a.abort_flag = 0; }
+    if (o == 0 && tid == 0) { *a.q_head = 0; *a.q_tail = a.total_tiles0; *a.done_objects = a.n_bad; *a.band_rows_total = 0; *a.valid_rows_total = 0ull; *a.abort_flag = 0; }
   }
 }
 
@@ -598,6 +664,7 @@ struct ScanArgs {
   float th;
   int D;
   int n_obj;
+  const int* vpre;        // persistent kernel: sdf values are stored compactly per ray (valid_sample_ranges); nullptr = n_rays x D
 };
 
 constexpr int kScanThreads = 1024;
@@ -619,6 +686,16 @@ __device__ __forceinline__ void ray_load(const ScanArgs& a, const ObjMeta& M, in
   for (int h = 0; h < 2; ++h) {
     const int j = lane + 32 * h;
     s[h] = (j < a.D) ? __ldcg(srow + j) : INFINITY;  // written by other CTAs (L2 is the point of coherence)
+  }
+}
+
+// same for the compact layout: the ray's hull [j0, j0 + cnt) starts at sample slot `p` of the object
+__device__ __forceinline__ void ray_load_compact(const ScanArgs& a, const ObjMeta& M, int p, int j0, int cnt, int lane, float s[2]) {
+  const float* srow = a.sdf + (size_t)M.smp_off + (size_t)p;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int k = lane + 32 * h - j0;
+    s[h] = (k >= 0 && k < cnt) ? __ldcg(srow + k) : INFINITY;
   }
 }
 
@@ -724,10 +801,16 @@ __device__ inline void scan_chunk(const ScanArgs& a, int* seg_cnt, const int o, 
   ScanState st;
   load_scan_state(a.state[o], st);
   float sv[kSegRays][2];
+  // compact sdf layout: lanes 0..8 fetch the segment's 9 range words once
+  int vw = 0;
+  if (a.vpre != nullptr && lane <= kSegRays && ray0 + lane <= M.n_rays) vw = __ldcg(a.vpre + vpre_base(M, o) + ray0 + lane);
 #pragma unroll
   for (int i = 0; i < kSegRays; ++i) {
-    if (ray0 + i < M.n_rays) ray_load(a, M, ray0 + i, lane, sv[i]);
-    else { sv[i][0] = INFINITY; sv[i][1] = INFINITY; }
+    const int v0 = __shfl_sync(0xffffffffu, vw, i), v1 = __shfl_sync(0xffffffffu, vw, i + 1);
+    if (ray0 + i < M.n_rays) {
+      if (a.vpre != nullptr) ray_load_compact(a, M, v0 >> 7, v0 & 127, (v1 >> 7) - (v0 >> 7), lane, sv[i]);
+      else ray_load(a, M, ray0 + i, lane, sv[i]);
+    } else { sv[i][0] = INFINITY; sv[i][1] = INFINITY; }
   }
   int count = 0;
   const size_t base = (size_t)M.smp_off + (size_t)ray0 * a.D;

@@ -199,6 +199,7 @@ struct TcSmemTail {
   uint32_t maskw[8 * 8 * kTcRows];        // ReLU masks [layer][32-col word][row]
   float bias[9 * kHid];
   float wlast[kHid];
+  float w0x[3 * kHid];                    // xyz rows of the layer-0 matrix (the latent rows are folded into ObjState.zb0)
   float zs[kMaxCode + 16];                // latent code of the tile's object (zero padded)
   float xr[3 * kTcRows];                  // object-frame point of every row
   float rr[kTcRows], rsc[kTcRows];
@@ -214,7 +215,7 @@ struct TcSmemTail {
   // persistent mode: copies of the kernel arguments for the out-of-line solve step.  Passing references to the kernel
   // parameters themselves would make them address-taken: the compiler then parks all of them in local memory and the tile
   // loop reads its pointers with LDL instead of from the constant bank.
-  MegaArgs ctx_q; SolveArgs ctx_sv; int ctx_D;
+  MegaArgs ctx_q; SolveArgs ctx_sv; int ctx_D; const float* ctx_rays;
   int push_base, push_nF, push_nS;        // cooperative publication of an object's next-iteration tiles
 };
 constexpr size_t kTcSmemBytes = 1024 + (size_t)kTcStages * kTcStageBytes + sizeof(TcSmemTail);
@@ -258,18 +259,22 @@ struct TileRef { int o, row0, slot, mode, tile; };
 // context of the whole process (the detectors on the Tracking thread live in it too).
 constexpr unsigned long long kMegaTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;
 __device__ inline int mega_pop(const MegaArgs& q, int n_obj) {
-  const int t = atomicAdd(q.q_head, 1);
-  if (t >= q.q_cap) return -1;
-  unsigned long long t0 = 0;
-  for (unsigned spins = 0;; ++spins) {
-    if (ldv(q.q_flag + t) != 0) { __threadfence(); return ldv(q.q_items + t); }
-    if (ldv(q.done_objects) >= n_obj || ldv(q.abort_flag) != 0) return -1;
-    __nanosleep(256);
-    if ((spins & 1023u) == 1023u) {
-      const unsigned long long now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > kMegaTimeoutNs) { atomicExch(q.abort_flag, 1); return -1; }
+  for (;;) {
+    const int t = atomicAdd(q.q_head, 1);
+    if (t >= q.q_cap) return -1;
+    unsigned long long t0 = 0;
+    int item = kItemNop;
+    for (unsigned spins = 0;; ++spins) {
+      if (ldv(q.q_flag + t) != 0) { __threadfence(); item = ldv(q.q_items + t); break; }
+      if (ldv(q.done_objects) >= n_obj || ldv(q.abort_flag) != 0) return -1;
+      __nanosleep(256);
+      if ((spins & 1023u) == 1023u) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > kMegaTimeoutNs) { atomicExch(q.abort_flag, 1); return -1; }
+      }
     }
+    if (item != kItemNop) return item;       // filler of a reserved slot that was not needed: take the next ticket
   }
 }
 
@@ -304,9 +309,10 @@ __device__ __forceinline__ bool tile_at(const TermArgs& a, TcSmemTail& S, int se
 }
 
 // rows of the term a tile belongs to (persistent kernel: the tile's own kind, counters written by other CTAs)
-__device__ __forceinline__ int mega_rows(const TermArgs& a, const ObjMeta& M, int o, int mode) {
+__device__ __forceinline__ int mega_rows(const TermArgs& a, const MegaArgs& q, const ObjMeta& M, int o, int mode) {
   if (mode == MODE_SDF) return M.n_pts;
   if (mode == MODE_BAND) return ldv(a.band_m + o);
+  if (q.vpre != nullptr) return ldv(q.vpre + vpre_base(M, o) + M.n_rays) >> 7;   // valid-sample hulls only
   return M.n_rays * a.D;
 }
 
@@ -331,6 +337,13 @@ __device__ __noinline__ void mega_solve_and_advance(TcSmemTail& S, int o, int ti
   if (tid == 0) mega_event(q, EV_SOLVE_BEGIN, 0, o, it);
   const int fin = solve_object<true>(sv, o, tid, SM, it + 1 >= q.n_iters);
   epi_bar_sync();
+  // ---- the next iteration's ray samples: only the run of samples inside the unit sphere of every ray (new pose and
+  // depth range, written by the solve above).  `fin` is the same in every thread (shared-memory flags).
+  int vh = -1;
+  if (!fin && q.render && q.vpre != nullptr) {
+    const ObjMeta M = sv.meta[o];
+    if (M.n_rays > 0) vh = valid_sample_ranges<true>(M, sv.state[o], S.ctx_rays, S.ctx_D, q.vpre + vpre_base(M, o), tid, kTcEpiThreads, S.warp_tmp);
+  }
   // ---- publish: finished, or the tiles of the next iteration.  All 256 threads write the queue slots (one thread
   // pushing 176 ray tiles + their flags one by one took ~3 us on the single-object critical path).
   if (tid == 0) {
@@ -342,7 +355,7 @@ __device__ __noinline__ void mega_solve_and_advance(TcSmemTail& S, int o, int ti
     } else {
       const ObjMeta M = sv.meta[o];
       const int ntS = (M.n_pts + kTcRows - 1) / kTcRows;
-      const int ntF = q.render ? (M.n_rays * S.ctx_D + kTcRows - 1) / kTcRows : 0;
+      const int ntF = q.render ? ((vh >= 0 ? vh : M.n_rays * S.ctx_D) + kTcRows - 1) / kTcRows : 0;
       *reinterpret_cast<volatile int*>(q.obj_iter + o) = it + 1;
       *reinterpret_cast<volatile int*>(q.pending + o) = ntS + (ntF > 0 ? 1 : 0);
       *reinterpret_cast<volatile int*>(q.ray_left + o) = ntF;
@@ -387,7 +400,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
     for (int i = 0; i < 8; ++i) mbar_init(&S.a_ready[i], 4);
     S.cur_class = -1;
     S.fifo_pub = 0; S.epi_seq = 0; S.last_flag = 0;
-    if (MEGA) { S.ctx_q = q; S.ctx_sv = sv; S.ctx_D = a.D; }
+    if (MEGA) { S.ctx_q = q; S.ctx_sv = sv; S.ctx_D = a.D; S.ctx_rays = a.rays; }
     fence_barrier_init();
   }
   if (warp == 8) tc_alloc(&S.tmem_base, 512);
@@ -555,7 +568,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
       const int L = dec.L, in0 = dec.in0, n_lin = dec.n_lin;
       const bool has_skip = dec.latent_in >= 0;
       const bool fwd_only = (mode == MODE_RAYFWD || mode == MODE_PTSFWD);
-      const int nrows = min(kTcRows, (MEGA ? mega_rows(a, M, o, mode) : term_rows(a, o)) - row0);
+      const int nrows = min(kTcRows, (MEGA ? mega_rows(a, q, M, o, mode) : term_rows(a, o)) - row0);
       const int ns = fwd_only ? plan.n_fwd : plan.n_steps;
       const float huber_b = (RENDER && mode == MODE_BAND) ? a.huber_b1 : a.huber_b;
       float* const part = (RENDER && mode == MODE_BAND) ? a.part_r : a.part;
@@ -568,6 +581,8 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
       if (S.cur_class != M.class_id) {
         for (int i = tid; i < n_lin * kHid; i += kTcEpiThreads) S.bias[i] = dec.bias[i / kHid][i % kHid];
         for (int i = tid; i < kHid; i += kTcEpiThreads) S.wlast[i] = dec.w_last[i];
+        const float* __restrict__ w0g = dec.Wf[0] + (size_t)L * kHid;   // rows L..L+2 of the reduction-major layer-0 matrix
+        for (int i = tid; i < 3 * kHid; i += kTcEpiThreads) S.w0x[i] = w0g[i];
       }
       if (tid < kMaxCode + 16) S.zs[tid] = (tid < L) ? ldv(&ost.z[tid]) : 0.f;
       // layer 0 with the latent part folded into a per-object bias (ObjState.zb0, refreshed by k_init / the solve step);
@@ -583,6 +598,15 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
       }
       const int* segp = nullptr;
       int nseg = 0;
+      const bool compact = RENDER && mode == MODE_RAYFWD && q.vpre != nullptr;
+      if (compact) {
+        // the object's per-ray range words (<= 8193 ints) in the idle J tile: row -> (ray, sample) by binary search below
+        int* sp = reinterpret_cast<int*>(S.Jp);
+        const int* gp = q.vpre + vpre_base(M, o);
+        for (int i = tid; i <= M.n_rays; i += kTcEpiThreads) sp[i] = __ldcg(gp + i);
+        epi_bar_sync();
+        segp = sp;
+      }
       if (RENDER && mode == MODE_BAND) {
         // band rows live compacted per 8-ray segment: stage the object's segment prefix (<= 1025 ints) in the idle J tile
         nseg = (M.n_rays + kSegRays - 1) / kSegRays;
@@ -610,11 +634,16 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
           x0 = __ldcg(a.band_x + 3 * sidx); x1 = __ldcg(a.band_x + 3 * sidx + 1); x2 = __ldcg(a.band_x + 3 * sidx + 2);
           sc = __ldcg(a.band_s + sidx); res_in = __ldcg(a.band_r + sidx);
         } else {
-          const int ray = rr_ / a.D, j = rr_ - ray * a.D;
-          const float* q = a.rays + 3 * (size_t)(M.ray_off + ray);
+          int ray = rr_ / a.D, j = rr_ - ray * a.D;
+          if (compact) {
+            int lo = 0, hi = M.n_rays;                 // largest ray whose hull starts at or before this row
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((segp[mid] >> 7) <= rr_) lo = mid; else hi = mid; }
+            ray = lo; j = (segp[lo] & 127) + (rr_ - (segp[lo] >> 7));
+          }
+          const float* rq = a.rays + 3 * (size_t)(M.ray_off + ray);
           const float d = lin_depth(ldv(&ost.dmin), ldv(&ost.dmax), ldv(&ost.dstep), j, a.D);
-          xform_point(Toc, __fmul_rn(q[0], d), __fmul_rn(q[1], d), __fmul_rn(q[2], d), x0, x1, x2);
-          sc = (sqrtf(x0 * x0 + x1 * x1 + x2 * x2) < 1.0f) ? 1.f : 0.f;
+          xform_point(Toc, __fmul_rn(rq[0], d), __fmul_rn(rq[1], d), __fmul_rn(rq[2], d), x0, x1, x2);
+          sc = inside_unit_sphere(x0, x1, x2) ? 1.f : 0.f;            // loss.py:68
         }
       }
       if (grp == 0) { S.xr[r] = x0; S.xr[kTcRows + r] = x1; S.xr[2 * kTcRows + r] = x2; }
@@ -635,7 +664,9 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         const uint32_t a_t = tmem + (uint32_t)s0.a_reg * 256u + lane_addr;
         const int kk = s0.k_steps * 16;
         const int n0out = dec.out_dim[0];
-        const float* __restrict__ w0x = dec.Wf[0] + (size_t)L * kHid;      // rows L..L+2 of the reduction-major layer-0 matrix
+        // (the three weight rows come from shared memory: as 768 uniform __ldg per thread and tile they were 6k L1
+        //  wavefronts per tile, most of the 8 us between a tile's begin and its first MMA)
+        const float* w0x = S.w0x;
         const float px = x0, py = x1, pz = x2;
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
@@ -647,9 +678,9 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
             for (int i = 0; i < 32; ++i) {
               const int c = n0 + i;
               float w = S.bias[c];
-              w = fmaf(__ldg(w0x + c), px, w);
-              w = fmaf(__ldg(w0x + kHid + c), py, w);
-              w = fmaf(__ldg(w0x + 2 * kHid + c), pz, w);
+              w = fmaf(w0x[c], px, w);
+              w = fmaf(w0x[kHid + c], py, w);
+              w = fmaf(w0x[2 * kHid + c], pz, w);
               const bool on = (c < n0out) && (w > 0.f);
               mw |= (on ? 1u : 0u) << i;
               t[i] = on ? w : 0.f;
@@ -935,6 +966,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
           // every ray sample of the object has its sdf value: the per-ray scan becomes 64-ray work items of its own
           if (tid == 0) {
             const int nch = (M.n_rays + kScanChunkRays - 1) / kScanChunkRays;
+            atomicAdd(q.valid_rows_total, (unsigned long long)ldv(a.V_count + o));      // V of this iteration is complete (roofline accounting)
             *reinterpret_cast<volatile int*>(q.scan_left + o) = nch;
             __threadfence();
             mega_push(q, kKindScan, o, nch);

@@ -178,8 +178,10 @@ const float* dspgn_results_device(DspgnSolver* s);
 int dspgn_decode_sdf(DspgnSolver* s, int class_id, const float* code, const float* x, int n,
                      int x_rs, int x_cs, float* sdf_out);
 
-/* Counters of the last run (for roofline arithmetic): decoder rows evaluated fwd+bwd and fwd-only,
- * and the number of kernel launches issued. */
+/* Counters of the last run (for roofline arithmetic): decoder rows evaluated fwd+bwd (SDF rows + band rows) and
+ * fwd-only, and the number of kernel launches issued.  Persistent schedule: fwd-only rows = the sum of V over objects
+ * and iterations, i.e. the ray samples inside the unit sphere, which is what the reference decodes (loss.py:68,77-78);
+ * one-launch-per-term schedule: every n_rays x D sample it evaluates. */
 typedef struct {
   int64_t rows_fwd_bwd;
   int64_t rows_fwd_only;

@@ -582,11 +582,8 @@ def test_code_len_shorter_than_latent_size(engine, dec_path, cfg_kitti, oracle, 
     assert r.is_good and r.code.shape == (32,)
 
 
-def test_render_term_through_persistent_kernel(dec_path, cfg_kitti, oracle, oracle_decoders):
-    """The joint run WITH the render term (what LocalMapping actually calls, src/LocalMapping_util.cc:179-180) inside the
-    persistent kernel: ray-sample tiles -> in-kernel per-ray scan -> band tiles -> SDF tiles -> solve as queue items.
-    Ragged mixed-class batch incl. an object without rays (soft failure) and one whose rays miss the object;
-    <= 3 kernel launches for all iterations, and results BIT-IDENTICAL to the one-launch-per-term schedule."""
+def _ragged_render_batch(cfg_kitti):
+    """Ragged mixed-class batch with rays: incl. an object without rays and one whose rays all miss the object."""
     import copy
     from dsp_slam_b200 import synth
     cfg = copy.deepcopy(cfg_kitti)
@@ -603,6 +600,46 @@ def test_render_term_through_persistent_kernel(dec_path, cfg_kitti, oracle, orac
             d.update(rays=np.zeros((0, 3), np.float32), depth=np.zeros(0, np.float32))
         ins.append(d)
     ins[6] = dict(ins[6], rays=np.asfortranarray(np.array(ins[6]["rays"]) * np.array([[-1, -1, 1]], np.float32) + np.array([[3, 3, 0]], np.float32)))
+    return cfg, objs, ins
+
+
+def test_valid_sample_hulls_equal_full_ray_enumeration(dec_path, cfg_kitti, monkeypatch):
+    """loss.py:68,77-78: the reference decodes only the V ray samples inside the unit sphere.  The persistent kernel's
+    forward-only tiles enumerate, per ray, the run [first valid, last valid] of its D samples (recomputed on the device after
+    every pose update) instead of all n_rays x D.  Same samples, same values: results, V and the band row counts are
+    BIT-IDENTICAL to the full enumeration (DSPGN_COMPACT_RAYS=0), incl. the object whose rays all miss (no ray tile at
+    all -> V = 0 -> soft failure) and the one without rays; the fwd-only row counter reports the same sum of V."""
+    cfg, objs, ins = _ragged_render_batch(cfg_kitti)
+    opt = _engine_or_skip("tc", dec_path["cars"], cfg, extra_decoders=[dec_path["chairs"]])
+    rs = opt.reconstruct_batch(ins)
+    c1 = opt.solver.counters()
+    monkeypatch.setenv("DSPGN_COMPACT_RAYS", "0")
+    opt0 = _engine_or_skip("tc", dec_path["cars"], cfg, extra_decoders=[dec_path["chairs"]])
+    monkeypatch.delenv("DSPGN_COMPACT_RAYS")
+    rs0 = opt0.reconstruct_batch(ins)
+    c0 = opt0.solver.counters()
+    assert c1["kernel_launches"] <= 3 and c0["kernel_launches"] <= 3
+    assert [r.is_good for r in rs] == [True, True, True, True, True, False, False, True]
+    for a_, b_ in zip(rs, rs0):
+        assert a_.is_good == b_.is_good and a_.status == b_.status and a_.loss == b_.loss
+        if a_.is_good:
+            assert a_.n_valid == b_.n_valid and a_.n_band == b_.n_band
+            np.testing.assert_array_equal(a_.t_cam_obj, b_.t_cam_obj)
+            np.testing.assert_array_equal(a_.code, b_.code)
+    # roofline accounting: fwd-only rows = sum of V over objects and iterations, the same either way, and well below
+    # n_rays x D x iterations (oracle: 81 % of this batch's samples lie inside the unit sphere)
+    full = sum(int(np.asarray(d["rays"]).shape[0]) for d in ins) * 50 * 6
+    assert c1["rows_fwd_only"] == c0["rows_fwd_only"] and 0 < c1["rows_fwd_only"] < 0.9 * full, (c1, c0, full)
+    assert c1["rows_fwd_bwd"] == c0["rows_fwd_bwd"]
+    assert rs[7].n_valid > 10
+
+
+def test_render_term_through_persistent_kernel(dec_path, cfg_kitti, oracle, oracle_decoders):
+    """The joint run WITH the render term (what LocalMapping actually calls, src/LocalMapping_util.cc:179-180) inside the
+    persistent kernel: ray-sample tiles -> in-kernel per-ray scan -> band tiles -> SDF tiles -> solve as queue items.
+    Ragged mixed-class batch incl. an object without rays (soft failure) and one whose rays miss the object;
+    <= 3 kernel launches for all iterations, and results BIT-IDENTICAL to the one-launch-per-term schedule."""
+    cfg, objs, ins = _ragged_render_batch(cfg_kitti)
     opt = _engine_or_skip("tc", dec_path["cars"], cfg, extra_decoders=[dec_path["chairs"]])
     rs = opt.reconstruct_batch(ins)
     c1 = opt.solver.counters()
