@@ -95,7 +95,7 @@ struct DspgnSolver {
   DevBuf d_state, d_part_s, d_part_r, d_tbase, d_V, d_m, d_results, d_active;
   DevBuf d_sdf, d_bx, d_bs, d_br;
   DevBuf d_dbg;
-  DevBuf d_q_items, d_q_flag, d_q_ctr, d_tiles_left, d_obj_iter;   // persistent-kernel work queue
+  DevBuf d_q_flag, d_q_ctr, d_tiles_left, d_obj_iter;   // persistent-kernel work queue
   int* d_tbase_static = nullptr;   // [n_obj] first 128-row SDF tile of each object (inside the staging block)
   int* d_tbase_r_static = nullptr; // [n_obj] first band-tile partial slot of each object (capacity: its ray-sample tiles + 1)
   int* d_q0_render = nullptr;      // [n_obj] first iteration-0 queue slot of each object in a run with the render term
@@ -104,6 +104,7 @@ struct DspgnSolver {
   int max_tiles128 = 0;            // largest tile count of one term of one object (queue items hold 19 bits)
   bool mega_enabled = true;
   bool compact_rays = true;        // persistent kernel, render term: forward-only tiles over the valid-sample hulls only (env DSPGN_COMPACT_RAYS=0: all n_rays x D samples)
+  bool vpre_exact = false;         // env DSPGN_VPRE_EXACT=1: exhaustive valid-range pre-pass (A/B switch)
   DevBuf d_clk, d_ev, d_seg, d_ln, d_vpre;
   bool clk_on = false;
   HostBuf h_results;
@@ -319,6 +320,7 @@ int dspgn_solver_create(const DspgnConfig* cfg, DspgnDecoder* const* classes, in
   if (int rc = tc_setup_kernels(g_err)) { dspgn_solver_destroy(s); return rc; }
   if (const char* m = getenv("DSPGN_MEGA")) s->mega_enabled = (m[0] != '0');
   if (const char* m = getenv("DSPGN_COMPACT_RAYS")) s->compact_rays = (m[0] != '0');   // A/B switch of the valid-sample hulls
+  if (const char* m = getenv("DSPGN_VPRE_EXACT")) s->vpre_exact = (m[0] != '0');
   if (cfg->schedule == DSPGN_SCHED_LAUNCHES) s->mega_enabled = false;
   else if (cfg->schedule == DSPGN_SCHED_PERSISTENT) s->mega_enabled = true;
   else if (cfg->schedule != DSPGN_SCHED_AUTO) { dspgn_solver_destroy(s); return fail(DSPGN_E_ARG, "bad schedule"); }
@@ -351,7 +353,7 @@ void dspgn_solver_destroy(DspgnSolver* s) {
   cudaDeviceSynchronize();
   dspgn_gather_close(s);
   for (DevBuf* b : {&s->d_decs, &s->d_stage, &s->d_state, &s->d_part_s, &s->d_part_r, &s->d_tbase, &s->d_V, &s->d_m, &s->d_results, &s->d_active,
-                    &s->d_sdf, &s->d_bx, &s->d_bs, &s->d_br, &s->d_dbg, &s->d_clk, &s->d_q_items, &s->d_q_flag, &s->d_q_ctr,
+                    &s->d_sdf, &s->d_bx, &s->d_bs, &s->d_br, &s->d_dbg, &s->d_clk, &s->d_q_flag, &s->d_q_ctr,
                     &s->d_tiles_left, &s->d_obj_iter, &s->d_ev, &s->d_seg, &s->d_ln, &s->d_vpre}) b->release();
   s->h_stage.release();
   s->h_results.release();
@@ -600,12 +602,13 @@ int launch_init(DspgnSolver* s, int pose_only, bool mega = false, bool render = 
   if (mega) {
     ia.render = render ? 1 : 0;
     ia.q0_off = render ? s->d_q0_render : s->d_tbase_static; ia.tile_rows = kTcRows;
-    ia.q_items = s->d_q_items.as<int>(); ia.q_flag = s->d_q_flag.as<int>();
+    ia.q_flag = s->d_q_flag.as<int>();
     ia.q_head = s->d_q_ctr.as<int>(); ia.q_tail = s->d_q_ctr.as<int>() + 32; ia.done_objects = s->d_q_ctr.as<int>() + 64;
     ia.band_rows_total = s->d_q_ctr.as<int>() + 80; ia.abort_flag = s->d_q_ctr.as<int>() + 96;
     ia.pending = s->d_tiles_left.as<int>(); ia.ray_left = s->d_tiles_left.as<int>() + s->n_obj;
     ia.obj_iter = s->d_obj_iter.as<int>();
     ia.total_tiles0 = s->total_tiles128 + (render ? (int)s->total_ray_tiles128 : 0);
+    ia.vpre_exact = s->vpre_exact ? 1 : 0;
     ia.rays = s->d_rays; ia.vpre = (render && s->compact_rays) ? s->d_vpre.as<int>() : nullptr;
     ia.valid_rows_total = reinterpret_cast<unsigned long long*>(s->d_q_ctr.as<int>() + 88);
   }
@@ -622,6 +625,7 @@ ScanArgs base_scan(DspgnSolver* s) {
   sa.sdf = s->d_sdf.as<float>(); sa.band_x = s->d_bx.as<float>(); sa.band_s = s->d_bs.as<float>();
   sa.band_r = s->d_br.as<float>(); sa.band_m = s->d_m.as<int>(); sa.th = c.cut_off; sa.D = c.num_depth_samples;
   sa.n_obj = s->n_obj;
+  sa.V_count = s->d_V.as<int>();
   return sa;
 }
 
@@ -712,7 +716,6 @@ int run_batch_impl(DspgnSolver* s, int mode) {
     // ---- persistent object-pipelined kernel: every GN iteration of every object in ONE launch --------------
     const int cap = (int)(items_per_iter * iters);
     int bad = 0;
-    bad |= s->d_q_items.reserve(4 * (size_t)cap);
     bad |= s->d_q_flag.reserve(4 * (size_t)cap);
     bad |= s->d_q_ctr.reserve(4 * 128);
     bad |= s->d_tiles_left.reserve(4 * 3 * (size_t)s->n_obj);
@@ -733,7 +736,7 @@ int run_batch_impl(DspgnSolver* s, int mode) {
     if (pose_only && iters > 5) { a.pt_active_out = s->d_active.as<uint8_t>(); a.cut_iter = 4; }
     MegaArgs q{};
     q.n_iters = iters; q.q_cap = cap; q.render = render ? 1 : 0;
-    q.q_items = s->d_q_items.as<int>(); q.q_flag = s->d_q_flag.as<int>();
+    q.q_flag = s->d_q_flag.as<int>();
     q.q_head = s->d_q_ctr.as<int>(); q.q_tail = s->d_q_ctr.as<int>() + 32; q.done_objects = s->d_q_ctr.as<int>() + 64;
     q.band_rows_total = s->d_q_ctr.as<int>() + 80;
     q.abort_flag = s->d_q_ctr.as<int>() + 96;
@@ -742,6 +745,7 @@ int run_batch_impl(DspgnSolver* s, int mode) {
     q.seg_cnt = s->d_seg.as<int>(); q.seg_prefix = s->d_seg.as<int>() + nseg_cap;
     q.valid_rows_total = reinterpret_cast<unsigned long long*>(s->d_q_ctr.as<int>() + 88);
     q.vpre = (render && s->compact_rays) ? s->d_vpre.as<int>() : nullptr;
+    q.vpre_exact = s->vpre_exact ? 1 : 0;
     if (s->clk_on) {
       if (s->d_ev.reserve(8 * (1 + 2 * (size_t)kEvCap))) return fail(DSPGN_E_ALLOC, "cudaMalloc");
       CU(cudaMemsetAsync(s->d_ev.p, 0, 8, s->stream));

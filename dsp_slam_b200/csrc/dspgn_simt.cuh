@@ -68,19 +68,20 @@ struct TermArgs {
 
 // Device work queue of the persistent object-pipelined kernel (dspgn_tc.cuh).
 // item = kind << 29 | object << 19 | tile   (kind: the tile's MODE_*; object < 1024; tile < 2^19; always >= 0)
+// A queue slot is ONE word: 0 = not published yet, item + 1 = published (payload and flag in one store / one load).
 constexpr int kItemKindShift = 29, kItemObjShift = 19, kItemTileMask = (1 << 19) - 1, kItemObjMask = 1023;
 constexpr int kKindScan = 3;   // queue-only kind: per-ray scan of a 64-ray chunk (no GEMM steps); 0..2 = MODE_SDF / MODE_BAND / MODE_RAYFWD
 __host__ __device__ __forceinline__ int make_item(int kind, int o, int tile) {
   return (kind << kItemKindShift) | (o << kItemObjShift) | tile;
 }
 // filler for reserved queue slots that turned out not to be needed (k_init reserves every object's iteration-0 slots
-// from host-side upper bounds): consumers skip it.  Never a real item: a scan item's tile index is < 128.
-constexpr int kItemNop = 0x7fffffff;
+// from host-side upper bounds): consumers skip it.  Never a real item (a scan item's tile index is < 128); + 1 fits an int.
+constexpr int kItemNop = 0x7ffffffe;
 struct MegaArgs {
   int n_iters;               // GN iterations per object
   int q_cap;                 // total items that can ever be pushed
   int render;                // 1: joint run with the render term (ray-sample tiles -> per-ray scan -> band tiles)
-  int* q_items; int* q_flag; // item payload / published flag per slot (no wrap-around)
+  int* q_flag;               // one word per slot (no wrap-around): 0 = empty, item + 1 = published
   int* q_head; int* q_tail;  // consumer ticket counter / producer reservation counter
   int* pending;              // [n_obj] SDF + band tiles of the object's current iteration still running (+1 while the
                              //         render term has not been expanded into band tiles yet)
@@ -91,6 +92,7 @@ struct MegaArgs {
   int* done_objects;         // objects finished (last iteration or frozen)
   int* band_rows_total;      // sum of band rows over all objects and iterations (roofline accounting)
   unsigned long long* valid_rows_total;   // sum of V (ray samples inside the unit sphere) over all objects and iterations
+  int vpre_exact;            // 1: the range pre-pass tests all D samples of every ray (debug / A-B switch)
   int* vpre;                 // per ray: (exclusive prefix of the valid-sample hulls << 7) | first valid sample, n_rays + 1
                              // entries per object at ray_off + o (dspgn_solve.cuh: valid_sample_ranges); nullptr = the
                              // forward-only tiles enumerate all n_rays * D samples

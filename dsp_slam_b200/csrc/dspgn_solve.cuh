@@ -160,6 +160,12 @@ __global__ void k_build_inputs(BuildArgs a) {
 //   vpre[ray] = (exclusive prefix of the hull lengths << 7) | first valid sample,   vpre[n_rays] = total << 7.
 // Sample positions and the inside test are the tile prologue's own (lin_depth, xform_point, inside_unit_sphere), so a hull
 // contains exactly the samples the full enumeration marks valid; the prologue still tests every row it is given.
+// Only the samples next to the two ends of a hull are actually tested: the chord of the ray inside the unit ball
+// (|u d + t| < 1 with u = R_oc q) brackets the hull to within a fraction of a sample, the search window is that bracket
+// +- 2 samples, found ends are extended outwards while the neighbour is valid, and a ray with an empty window is scanned
+// completely unless its line misses the ball by more than 1 % of the radius -- so the result is the hull of the exhaustive
+// test (`exact` = 1, env DSPGN_VPRE_EXACT: no bracket, the whole sample range is searched from both ends; testing all D
+// samples of every ray cost 12 us per solve on 450 rays).
 // Called by all `nthreads` (multiple of 32, <= 1024) threads; s_wsum: 32 ints of shared memory.  Returns the total.
 __device__ __forceinline__ int vpre_base(const ObjMeta& M, int o) { return M.ray_off + o; }
 template <bool NAMED_BAR>
@@ -169,7 +175,7 @@ __device__ __forceinline__ void vpre_sync() {
 }
 template <bool NAMED_BAR>
 __device__ inline int valid_sample_ranges(const ObjMeta& M, const ObjState& st, const float* __restrict__ rays, const int D,
-                                          int* vp, const int tid, const int nthreads, int* s_wsum) {
+                                          int* vp, const int tid, const int nthreads, int* s_wsum, const bool exact) {
   const int lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
   float T[12];
 #pragma unroll
@@ -182,13 +188,45 @@ __device__ inline int valid_sample_ranges(const ObjMeta& M, const ObjState& st, 
     if (ray < M.n_rays) {
       const float* q = rays + 3 * (size_t)(M.ray_off + ray);
       const float q0 = q[0], q1 = q[1], q2 = q[2];
-      int lo = -1, hi = -1;
-#pragma unroll 5
-      for (int j = 0; j < D; ++j) {             // independent samples: unrolled for instruction-level parallelism
+      auto valid = [&](int j) -> bool {           // exactly the tile prologue's test of sample j
         const float d = lin_depth(dmin, dmax, dstep, j, D);
         float x, y, z;
         xform_point(T, __fmul_rn(q0, d), __fmul_rn(q1, d), __fmul_rn(q2, d), x, y, z);
-        if (inside_unit_sphere(x, y, z)) { if (lo < 0) lo = j; hi = j; }
+        return inside_unit_sphere(x, y, z);
+      };
+      int w0 = 0, w1 = D - 1;                     // search window (inclusive)
+      bool none = false;
+      const float ux = T[0] * q0 + T[1] * q1 + T[2] * q2, uy = T[4] * q0 + T[5] * q1 + T[6] * q2, uz = T[8] * q0 + T[9] * q1 + T[10] * q2;
+      const float aa = ux * ux + uy * uy + uz * uz, bb = ux * T[3] + uy * T[7] + uz * T[11];
+      const float cc = T[3] * T[3] + T[7] * T[7] + T[11] * T[11] - 1.0f;
+      if (!exact && aa > 1e-20f && aa < 1e20f && dstep > 1e-12f && fabsf(dmin) < 1e4f && fabsf(dmax) < 1e4f && fabsf(bb) < 1e20f && fabsf(cc) < 1e20f) {
+        const float inv = 1.0f / aa;
+        if (cc - bb * bb * inv > 0.02f) none = true;          // closest approach > 1.01: no sample can test inside
+        else {
+          const float sq = sqrtf(fmaxf(bb * bb - aa * cc, 0.f)) * inv, dc = -bb * inv;
+          const float flo = (dc - sq - dmin) / dstep, fhi = (dc + sq - dmin) / dstep;      // chord ends in sample units
+          if (flo == flo && fhi == fhi) {                      // (NaN: keep the full window)
+            if (fhi < -2.0f || flo > (float)(D + 1)) none = true;   // the chord ends two samples before the first / starts two after the last
+            else {
+              w0 = max(0, (int)floorf(fmaxf(flo, -4.0f)) - 2);
+              w1 = min(D - 1, (int)ceilf(fminf(fhi, (float)(D + 4))) + 2);
+            }
+          }
+        }
+      }
+      int lo = -1, hi = -1;
+      if (!none) {
+        for (int j = w0; j <= w1; ++j) if (valid(j)) { lo = j; break; }
+        if (lo < 0 && (w0 > 0 || w1 < D - 1)) {                 // nothing next to the chord (not expected): test every sample
+          w1 = D - 1;
+          for (int j = 0; j < D; ++j) if (valid(j)) { lo = j; break; }
+        }
+        if (lo >= 0) {
+          while (lo > 0 && valid(lo - 1)) --lo;
+          hi = lo;
+          for (int j = w1; j > lo; --j) if (valid(j)) { hi = j; break; }
+          while (hi < D - 1 && valid(hi + 1)) ++hi;
+        }
       }
       if (lo >= 0) { first = lo; cnt = hi - lo + 1; }
     }
@@ -217,13 +255,14 @@ struct InitArgs {
   uint8_t* pt_active;      // [total_pts] reset to 1 (pose-only mode)
   int n_obj, code_len, D, pose_only;
   // persistent-kernel mode: also seed the work queue with every object's iteration-0 tiles (ray-sample tiles first)
-  int mega; int render; const int* q0_off; int tile_rows; int* q_items; int* q_flag; int* q_head; int* q_tail;
+  int mega; int render; const int* q0_off; int tile_rows; int* q_flag; int* q_head; int* q_tail;
   int* pending; int* ray_left; int* obj_iter; int* done_objects; int* band_rows_total; int* abort_flag; int total_tiles0;
   GatherDev gather;
   float* results;          // records of objects rejected at upload are written here
   int n_bad;
   const DecoderDev* decs;  // layer-0 fold (ObjState.zb0)
   unsigned long long* valid_rows_total;
+  int vpre_exact;
   const float* rays; int* vpre;   // render runs of the persistent kernel: valid-sample ranges (nullptr = off)
 };
 
@@ -274,13 +313,13 @@ __global__ void k_init(InitArgs a) {
     if (a.vpre != nullptr && ntF_cap > 0) {
       __shared__ int s_wsum[32];
       __syncthreads();                         // T_oc / depth range written by thread 0 above
-      const int vh = valid_sample_ranges<false>(M, st, a.rays, a.D, a.vpre + vpre_base(M, o), tid, blockDim.x, s_wsum);
+      const int vh = valid_sample_ranges<false>(M, st, a.rays, a.D, a.vpre + vpre_base(M, o), tid, blockDim.x, s_wsum, a.vpre_exact != 0);
       ntF = (vh + a.tile_rows - 1) / a.tile_rows;
     }
     const int base = a.q0_off[o];
-    for (int j = tid; j < ntF; j += blockDim.x) { a.q_items[base + j] = make_item(MODE_RAYFWD, o, j); a.q_flag[base + j] = 1; }
-    for (int j = tid; j < ntS; j += blockDim.x) { a.q_items[base + ntF + j] = make_item(MODE_SDF, o, j); a.q_flag[base + ntF + j] = 1; }
-    for (int j = ntF + ntS + tid; j < ntF_cap + ntS; j += blockDim.x) { a.q_items[base + j] = kItemNop; a.q_flag[base + j] = 1; }
+    for (int j = tid; j < ntF; j += blockDim.x) a.q_flag[base + j] = make_item(MODE_RAYFWD, o, j) + 1;
+    for (int j = tid; j < ntS; j += blockDim.x) a.q_flag[base + ntF + j] = make_item(MODE_SDF, o, j) + 1;
+    for (int j = ntF + ntS + tid; j < ntF_cap + ntS; j += blockDim.x) a.q_flag[base + j] = kItemNop + 1;
     if (tid == 0) { a.pending[o] = ntS + (ntF > 0 ? 1 : 0); a.ray_left[o] = ntF; a.obj_iter[o] = 0; }
     if (o == 0 && tid == 0) { *a.q_head = 0; *a.q_tail = a.total_tiles0; *a.done_objects = a.n_bad; *a.band_rows_total = 0; *a.valid_rows_total = 0ull; *a.abort_flag = 0; }
   }
@@ -665,6 +704,7 @@ struct ScanArgs {
   int D;
   int n_obj;
   const int* vpre;        // persistent kernel: sdf values are stored compactly per ray (valid_sample_ranges); nullptr = n_rays x D
+  int* V_count;           // persistent kernel: the scan items count V (samples with a finite sdf value) per object
 };
 
 constexpr int kScanThreads = 1024;
@@ -812,6 +852,13 @@ __device__ inline void scan_chunk(const ScanArgs& a, int* seg_cnt, const int o, 
       else ray_load(a, M, ray0 + i, lane, sv[i]);
     } else { sv[i][0] = INFINITY; sv[i][1] = INFINITY; }
   }
+  // V (loss.py:68,73): samples inside the unit sphere = the finite sdf values.  Counted here, one atomic per segment,
+  // instead of by the forward-only tiles (four contended atomics per tile, all tiles of a wave finishing together).
+  int nvalid = 0;
+#pragma unroll
+  for (int i = 0; i < kSegRays; ++i)
+    nvalid += __popc(__ballot_sync(0xffffffffu, sv[i][0] != INFINITY)) + __popc(__ballot_sync(0xffffffffu, sv[i][1] != INFINITY));
+  if (lane == 0 && nvalid != 0) atomicAdd(a.V_count + o, nvalid);
   int count = 0;
   const size_t base = (size_t)M.smp_off + (size_t)ray0 * a.D;
 #pragma unroll

@@ -217,6 +217,7 @@ struct TcSmemTail {
   // loop reads its pointers with LDL instead of from the constant bank.
   MegaArgs ctx_q; SolveArgs ctx_sv; int ctx_D; const float* ctx_rays;
   int push_base, push_nF, push_nS;        // cooperative publication of an object's next-iteration tiles
+  float ost[16]; int ost_rows;            // the tile's object: T_oc[12], dmin, dmax, dstep, dfar; rows of its term (counter)
 };
 constexpr size_t kTcSmemBytes = 1024 + (size_t)kTcStages * kTcStageBytes + sizeof(TcSmemTail);
 
@@ -265,7 +266,8 @@ __device__ inline int mega_pop(const MegaArgs& q, int n_obj) {
     unsigned long long t0 = 0;
     int item = kItemNop;
     for (unsigned spins = 0;; ++spins) {
-      if (ldv(q.q_flag + t) != 0) { __threadfence(); item = ldv(q.q_items + t); break; }
+      const int v = ldv(q.q_flag + t);
+      if (v != 0) { __threadfence(); item = v - 1; break; }
       if (ldv(q.done_objects) >= n_obj || ldv(q.abort_flag) != 0) return -1;
       __nanosleep(256);
       if ((spins & 1023u) == 1023u) {
@@ -316,13 +318,13 @@ __device__ __forceinline__ int mega_rows(const TermArgs& a, const MegaArgs& q, c
   return M.n_rays * a.D;
 }
 
-// publish `n` queue items (kind, object, tile 0..n-1): reserve slots, payload, fence, flags.  One thread.
+// publish `n` queue items (kind, object, tile 0..n-1): reserve slots, fence (everything the items depend on, incl. the
+// counters updated just before the call), one word per slot.  One thread.
 __device__ inline void mega_push(const MegaArgs& q, int kind, int o, int n) {
   if (n <= 0) return;
   const int base = atomicAdd(q.q_tail, n);
-  for (int j = 0; j < n; ++j) *reinterpret_cast<volatile int*>(q.q_items + base + j) = make_item(kind, o, j);
   __threadfence();
-  for (int j = 0; j < n; ++j) *reinterpret_cast<volatile int*>(q.q_flag + base + j) = 1;
+  for (int j = 0; j < n; ++j) *reinterpret_cast<volatile int*>(q.q_flag + base + j) = make_item(kind, o, j) + 1;
 }
 
 // all terms of the object's current iteration are in: solve, update, queue the next iteration (or finish).  Called by
@@ -342,24 +344,24 @@ __device__ __noinline__ void mega_solve_and_advance(TcSmemTail& S, int o, int ti
   int vh = -1;
   if (!fin && q.render && q.vpre != nullptr) {
     const ObjMeta M = sv.meta[o];
-    if (M.n_rays > 0) vh = valid_sample_ranges<true>(M, sv.state[o], S.ctx_rays, S.ctx_D, q.vpre + vpre_base(M, o), tid, kTcEpiThreads, S.warp_tmp);
+    if (M.n_rays > 0) vh = valid_sample_ranges<true>(M, sv.state[o], S.ctx_rays, S.ctx_D, q.vpre + vpre_base(M, o), tid, kTcEpiThreads, S.warp_tmp, q.vpre_exact != 0);
   }
   // ---- publish: finished, or the tiles of the next iteration.  All 256 threads write the queue slots (one thread
   // pushing 176 ray tiles + their flags one by one took ~3 us on the single-object critical path).
   if (tid == 0) {
     mega_event(q, EV_SOLVE_END, 0, o, it);
-    __threadfence();                         // state / result record before anything is published
     int base = -1;
     if (fin) {
+      __threadfence();                       // the result record before the object counts as done
       atomicAdd(q.done_objects, 1);
     } else {
+      // (no fence in this branch: q_tail only reserves slots; state and counters are fenced below, before any slot is published)
       const ObjMeta M = sv.meta[o];
       const int ntS = (M.n_pts + kTcRows - 1) / kTcRows;
       const int ntF = q.render ? ((vh >= 0 ? vh : M.n_rays * S.ctx_D) + kTcRows - 1) / kTcRows : 0;
       *reinterpret_cast<volatile int*>(q.obj_iter + o) = it + 1;
       *reinterpret_cast<volatile int*>(q.pending + o) = ntS + (ntF > 0 ? 1 : 0);
       *reinterpret_cast<volatile int*>(q.ray_left + o) = ntF;
-      __threadfence();
       base = atomicAdd(q.q_tail, ntF + ntS);  // the long chain (rays -> scan -> band -> solve) first, then the SDF tiles
       S.push_nF = ntF; S.push_nS = ntS;
     }
@@ -369,11 +371,10 @@ __device__ __noinline__ void mega_solve_and_advance(TcSmemTail& S, int o, int ti
   const int base = S.push_base;
   if (base >= 0) {
     const int nF = S.push_nF, n = nF + S.push_nS;
+    __threadfence();                          // this thread's share of the ray range words (thread 0: state, counters)
+    epi_bar_sync();                           // ... of every thread, before the first slot is published
     for (int j = tid; j < n; j += kTcEpiThreads)
-      *reinterpret_cast<volatile int*>(q.q_items + base + j) = (j < nF) ? make_item(MODE_RAYFWD, o, j) : make_item(MODE_SDF, o, j - nF);
-    __threadfence();
-    epi_bar_sync();                           // every item is written (and fenced) before the first flag goes up
-    for (int j = tid; j < n; j += kTcEpiThreads) *reinterpret_cast<volatile int*>(q.q_flag + base + j) = 1;
+      *reinterpret_cast<volatile int*>(q.q_flag + base + j) = ((j < nF) ? make_item(MODE_RAYFWD, o, j) : make_item(MODE_SDF, o, j - nF)) + 1;
   }
 }
 
@@ -546,6 +547,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
           epi_bar_sync();
           if (tid == 0) {
             __threadfence();                         // prefix / band_m / band rows before the band tiles are published
+            atomicAdd(q.valid_rows_total, (unsigned long long)ldv(sc_args.V_count + o));   // V of this iteration is complete (roofline accounting)
             const int m = ldv(sc_args.band_m + o);
             const int ntB = (m + kTcRows - 1) / kTcRows;
             atomicAdd(q.band_rows_total, m);
@@ -568,16 +570,19 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
       const int L = dec.L, in0 = dec.in0, n_lin = dec.n_lin;
       const bool has_skip = dec.latent_in >= 0;
       const bool fwd_only = (mode == MODE_RAYFWD || mode == MODE_PTSFWD);
-      const int nrows = min(kTcRows, (MEGA ? mega_rows(a, q, M, o, mode) : term_rows(a, o)) - row0);
       const int ns = fwd_only ? plan.n_fwd : plan.n_steps;
       const float huber_b = (RENDER && mode == MODE_BAND) ? a.huber_b1 : a.huber_b;
       float* const part = (RENDER && mode == MODE_BAND) ? a.part_r : a.part;
-      // the pose / code of this object may have been rewritten by another CTA's solve: bypass L1
-      float Toc[12];
-#pragma unroll
-      for (int i = 0; i < 12; ++i) Toc[i] = ldv(&ost.T_oc[i]);
+      // ---- prologue, phase A: everything that comes from global memory, then ONE barrier ------------------------------
+      // The pose / depth range of this object may have been rewritten by another CTA's solve: read (cache-bypassing) once
+      // per tile by 16 threads and shared through smem.  As 12 + 3 loads in every thread they were ~130 requests per tile
+      // for the same two L2 lines -- and on few-object batches every SM asks for them at the same moment.
+      if (tid < 12) S.ost[tid] = ldv(&ost.T_oc[tid]);
+      else if (tid < 16) S.ost[tid] = ldv(&ost.dmin + (tid - 12));          // dmin, dmax, dstep, dfar
+      const bool pts_mode = (mode == MODE_SDF || mode == MODE_PTSFWD);
+      if (MEGA && !pts_mode && tid == 16) S.ost_rows = mega_rows(a, q, M, o, mode);   // band / ray-sample rows: a counter
 
-      // ---- per-class constants in smem (bias, last row), the tile's latent code, this row's point ----
+      // per-class constants in smem (bias, last row, xyz rows of layer 0), the tile's latent code
       if (S.cur_class != M.class_id) {
         for (int i = tid; i < n_lin * kHid; i += kTcEpiThreads) S.bias[i] = dec.bias[i / kHid][i % kHid];
         for (int i = tid; i < kHid; i += kTcEpiThreads) S.wlast[i] = dec.w_last[i];
@@ -586,7 +591,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
       }
       if (tid < kMaxCode + 16) S.zs[tid] = (tid < L) ? ldv(&ost.z[tid]) : 0.f;
       // layer 0 with the latent part folded into a per-object bias (ObjState.zb0, refreshed by k_init / the solve step);
-      // written after the per-class reload above, read after the barrier below
+      // written after the per-class reload above, read after the barriers below
       S.bias[tid] = ldv(&ost.zb0[tid]);
       // pose-only inlier cut (optimizer.py:76-78): recorded while iteration `cut_iter` runs, applied afterwards
       const uint8_t* mask_in = a.pt_active;
@@ -604,25 +609,39 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
         int* sp = reinterpret_cast<int*>(S.Jp);
         const int* gp = q.vpre + vpre_base(M, o);
         for (int i = tid; i <= M.n_rays; i += kTcEpiThreads) sp[i] = __ldcg(gp + i);
-        epi_bar_sync();
         segp = sp;
       }
       if (RENDER && mode == MODE_BAND) {
-        // band rows live compacted per 8-ray segment: stage the object's segment prefix (<= 1025 ints) in the idle J tile
+        // band rows live compacted per ray segment: stage the object's segment prefix in the idle J tile
         nseg = (M.n_rays + kSegRays - 1) / kSegRays;
         int* sp = reinterpret_cast<int*>(S.Jp);
         const int* gp = q.seg_prefix + seg_base(M, o);
         for (int i = tid; i <= nseg; i += kTcEpiThreads) sp[i] = __ldcg(gp + i);
-        epi_bar_sync();
         segp = sp;
       }
-      float x0 = 0.f, x1 = 0.f, x2 = 0.f, sc = 0.f, res_in = 0.f;
+      // surface points do not depend on anything above: fetch them before the barrier
+      int nrows = 0;
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f, sc = 0.f;
+      if (pts_mode) {
+        nrows = min(kTcRows, (MEGA ? M.n_pts : term_rows(a, o)) - row0);
+        if (r < nrows) {
+          const float* pq = a.pts + 3 * (size_t)(M.pts_off + row0 + r);
+          p0 = pq[0]; p1 = pq[1]; p2 = pq[2];
+          sc = (mask_in == nullptr || ldv(mask_in + M.pts_off + row0 + r)) ? 1.f : 0.f;
+        }
+      }
+      epi_bar_sync();      // (per-iteration schedule: Jp / rr of the previous tile are not written before the barrier further down;
+                           //  persistent schedule: the previous tile ended with a barrier, its J tile is dead)
+      // ---- phase B: this row's point in the object frame ----------------------------------------------------------------
+      float Toc[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) Toc[i] = S.ost[i];
+      if (!pts_mode) nrows = min(kTcRows, (MEGA ? S.ost_rows : term_rows(a, o)) - row0);
+      float x0 = 0.f, x1 = 0.f, x2 = 0.f, res_in = 0.f;
       if (r < nrows) {
         const int rr_ = row0 + r;
-        if (mode == MODE_SDF || mode == MODE_PTSFWD) {
-          const float* q = a.pts + 3 * (size_t)(M.pts_off + rr_);
-          xform_point(Toc, q[0], q[1], q[2], x0, x1, x2);
-          sc = (mask_in == nullptr || ldv(mask_in + M.pts_off + rr_)) ? 1.f : 0.f;
+        if (pts_mode) {
+          xform_point(Toc, p0, p1, p2, x0, x1, x2);
         } else if (mode == MODE_BAND) {
           // band rows were written by the CTAs that ran this object's scan: L2 is the point of coherence
           size_t sidx = (size_t)M.smp_off + rr_;
@@ -641,7 +660,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
             ray = lo; j = (segp[lo] & 127) + (rr_ - (segp[lo] >> 7));
           }
           const float* rq = a.rays + 3 * (size_t)(M.ray_off + ray);
-          const float d = lin_depth(ldv(&ost.dmin), ldv(&ost.dmax), ldv(&ost.dstep), j, a.D);
+          const float d = lin_depth(S.ost[12], S.ost[13], S.ost[14], j, a.D);
           xform_point(Toc, __fmul_rn(rq[0], d), __fmul_rn(rq[1], d), __fmul_rn(rq[2], d), x0, x1, x2);
           sc = inside_unit_sphere(x0, x1, x2) ? 1.f : 0.f;            // loss.py:68
         }
@@ -739,7 +758,7 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
               const size_t base = (mode == MODE_RAYFWD) ? (size_t)M.smp_off : (size_t)M.pts_off;
               a.sdf_out[base + row0 + r] = (sc != 0.f) ? yv : INFINITY;
             }
-            if (mode == MODE_RAYFWD) {
+            if (!RENDER && mode == MODE_RAYFWD) {        // (persistent kernel: counted by the scan items, dspgn_solve.cuh)
               const unsigned b = __ballot_sync(0xffffffffu, grp == 0 && r < nrows && sc != 0.f);
               if (lane == 0 && b) atomicAdd(a.V_count + o, __popc(b));
             }
@@ -966,7 +985,6 @@ __device__ __forceinline__ void tc_body(const TermArgs& a, const MegaArgs& q, co
           // every ray sample of the object has its sdf value: the per-ray scan becomes 64-ray work items of its own
           if (tid == 0) {
             const int nch = (M.n_rays + kScanChunkRays - 1) / kScanChunkRays;
-            atomicAdd(q.valid_rows_total, (unsigned long long)ldv(a.V_count + o));      // V of this iteration is complete (roofline accounting)
             *reinterpret_cast<volatile int*>(q.scan_left + o) = nch;
             __threadfence();
             mega_push(q, kKindScan, o, nch);
