@@ -23,9 +23,10 @@
 // kernels, the CTA's scheduler (pops the device work queue).
 //
 // Three schedules share this body (template SCHED): 0 = one launch per term and iteration (k_decoder_tc), 1 = persistent
-// kernel with SDF tiles only (k_gn_persistent), 2 = persistent kernel with the render term: ray-sample tiles, 64-ray scan
-// items, band tiles, SDF tiles (k_gn_persistent_render).  The CTA that completes an object's last outstanding tile runs
-// its solve (dspgn_solve.cuh) and queues the next iteration.
+// kernel with SDF tiles only (k_gn_persistent), 2 = persistent kernel with the render term: ray-sample tiles (only the run
+// of samples inside the unit sphere of every ray: dspgn_solve.cuh, valid_sample_ranges), 64-ray scan items, band tiles,
+// SDF tiles (k_gn_persistent_render).  The CTA that completes an object's last outstanding tile runs its solve
+// (dspgn_solve.cuh), the next iteration's sample ranges, and queues the next iteration.
 //
 // Restates the same reference arithmetic as dspgn_simt.cuh (loss.py:22-43,143-150; loss_utils.py:51-103;
 // deep_sdf_decoder.py:75-110; optimizer.py:161-167).
