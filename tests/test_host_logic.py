@@ -281,3 +281,35 @@ def test_native_packer_equals_python_packer():
     mixed = [dict(t_cam_obj=np.eye(4).tolist(), pts=np.zeros((5, 3)))]
     arr, keep = bs._pack(mixed)
     assert arr[0].n_pts == 5 and isinstance(keep[0], tuple) and keep[0][1].dtype == np.float32    # converted copies are kept alive
+
+
+def test_shipped_library_is_tcgen05_code_for_sm_100a_only():
+    """The product path is hand-written tcgen05 / TMEM code for sm_100a (no mma.sync / wgmma recompiles, no second
+    architecture): disassemble the built library (cuobjdump, no GPU needed) and look for the opcodes that prove it
+    (B200_PROFILING.md: tcgen05.mma -> UTCHMMA, tcgen05.ld/st -> LDTM/STTM, cp.async.bulk -> UBLKCP) in every kernel
+    that runs decoder tiles; profiles/sass_summary.txt is the same listing per kernel."""
+    import re
+    import shutil
+    import subprocess
+    from dsp_slam_b200 import _lib
+    if shutil.which("cuobjdump") is None or not os.path.isfile(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    assert set(re.findall(r"arch = (sm_\w+)", out)) == {"sm_100a"}
+    per_kernel, kern = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            kern = m.group(1)
+            per_kernel[kern] = set()
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and kern:
+            per_kernel[kern].add(m.group(1))
+    tiles = [k for k in per_kernel if any(n in k for n in ("k_gn_persistent", "k_decoder_tc"))]
+    assert len(tiles) == 3, sorted(per_kernel)
+    for k in tiles:
+        ops = per_kernel[k]
+        assert {"UTCHMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP"} <= ops, (k, sorted(ops)[:40])
+    everything = set().union(*per_kernel.values())
+    assert not any(op.startswith(("HMMA", "HGMMA", "IMMA")) for op in everything)     # no legacy tensor-core paths anywhere
