@@ -313,3 +313,35 @@ def test_shipped_library_is_tcgen05_code_for_sm_100a_only():
         assert {"UTCHMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP"} <= ops, (k, sorted(ops)[:40])
     everything = set().union(*per_kernel.values())
     assert not any(op.startswith(("HMMA", "HGMMA", "IMMA")) for op in everything)     # no legacy tensor-core paths anywhere
+
+
+def test_ctypes_mirror_has_the_layout_of_the_c_header(tmp_path):
+    """The hand-written ctypes structures of dsp_slam_b200/_lib.py against include/dspgn.h as the C compiler lays it
+    out: a generated C program prints sizeof / offsetof of every field, gcc compiles it against the real header."""
+    import shutil
+    import subprocess
+    from dsp_slam_b200 import _lib
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    pairs = [("DspgnDecoderSpec", _lib.DecoderSpec), ("DspgnConfig", _lib.Config), ("DspgnObjectIn", _lib.ObjectIn),
+             ("DspgnObjectOut", _lib.ObjectOut), ("DspgnCounters", _lib.Counters), ("DspgnIpcHandle", _lib.IpcHandle)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dspgn.h"', 'int main(void) {']
+    for cname, st in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in st._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  printf("MAX_CODE %d MAX_LINEAR %d RESULT_FLOATS %d IPC %d\\n", DSPGN_MAX_CODE, DSPGN_MAX_LINEAR, '
+              'DSPGN_RESULT_FLOATS, DSPGN_IPC_HANDLE_BYTES);', '  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(line.rsplit(" ", 1) for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True)
+               .stdout.splitlines() if not line.startswith("MAX_CODE"))
+    for cname, st in pairs:
+        assert int(got[cname]) == C.sizeof(st), cname
+        for fname, _ in st._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(st, fname).offset, (cname, fname)
+    consts = subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines()[-1].split()
+    assert [int(consts[i]) for i in (1, 3, 5, 7)] == [_lib.MAX_CODE, _lib.MAX_LINEAR, _lib.RESULT_FLOATS, _lib.IPC_HANDLE_BYTES]
