@@ -196,3 +196,39 @@ def test_decoder_variants_vs_reference(oracle, golden_dir):
     np.testing.assert_allclose(g, st["jac_g"], rtol=0, atol=5e-6)
     J, res = oracle.sdf_term(dw, st["sdf_pts"], oracle.inv4(st["sdf_t_cam_obj"]), st["sdf_z"])
     assert rel(J, st["sdf_J"]) < 1e-5 and np.abs(res - st["sdf_res"]).max() < 3e-6
+
+
+def test_every_hyper_parameter_is_read_like_the_reference(oracle, oracle_decoders, cfg_kitti, golden_dir):
+    """`recon_hyper.npz`: a reference run with EVERY value of the `optimizer` block moved off the shipped configs (D = 24
+    depth samples, band half-width 0.02, k1..k4, b1, b2, learning rate, scale damping, 6 iterations) and the initial pose
+    tilted 3 degrees so that the rotation prior is active (optimizer.py:27-43,120-126,155-192; loss.py:84-141,155-178).
+    The restatement must read each of them where the reference does: the render counters V and m of every iteration, the
+    system of iteration 0 tightly (k4 |J_rot|^2 = 5.5 and s_damp = 2 against max |H| = 170: a wrong coefficient is a 1e-2
+    effect), later systems and the end state to the noise floor (measured: H 3.5e-3 at iteration 5, |dT| 5e-4, |dcode| 2e-3).
+    (This golden was added after the round's GPU budget was spent: it pins the oracle; the CUDA path has not been run on it.)"""
+    import copy
+    import json
+    d = np.load(os.path.join(golden_dir, "recon_hyper.npz"))
+    hyper = json.loads(bytes(d["hyper_json"]).decode())
+    cfgd = copy.deepcopy(cfg_kitti)
+    cfgd["optimizer"]["num_depth_samples"] = hyper["num_depth_samples"]
+    cfgd["optimizer"]["cut_off_threshold"] = hyper["cut_off_threshold"]
+    cfgd["optimizer"]["joint_optim"].update(hyper["joint_optim"])
+    cfg = oracle.GNConfig.from_json_dict(cfgd)
+    assert (cfg.num_depth_samples, cfg.num_iterations, cfg.cut_off, cfg.lr, cfg.s_damp, cfg.k4) == (24, 6, 0.02, 0.8, 2.0, 2000.0)
+    trace = []
+    out = oracle.reconstruct_object(oracle_decoders["cars"], cfg, d["in_t_cam_obj"], d["in_pts"], d["in_rays"], d["in_depth"],
+                                    trace=trace)
+    assert out["is_good"] and bool(d["is_good"]) and len(trace) == 6
+    V, m = np.array([t["V"] for t in trace]), np.array([t["m"] for t in trace])
+    assert V[0] == d["V_iters"][0] and m[0] == d["m_iters"][0]
+    assert np.abs(V - d["V_iters"]).max() <= 2 and np.abs(m - d["m_iters"]).max() <= 4      # boundary flips only
+    _, r_rot = oracle.rotation_prior(oracle.inv4(d["in_t_cam_obj"].astype(np.float32)))
+    assert r_rot > 1e-3                                                                     # the prior is active
+    assert rel(trace[0]["H"], d["H_iters"][0]) < 1e-4 and rel(trace[0]["b"], d["b_iters"][0]) < 1e-4
+    assert np.abs(trace[0]["dx"] - d["dx_iters"][0]).max() < 2e-5
+    for k in range(1, 6):
+        assert rel(trace[k]["H"], d["H_iters"][k]) < 2e-2 and np.abs(trace[k]["dx"] - d["dx_iters"][k]).max() < 1e-2, k
+    assert np.abs(out["t_cam_obj"] - d["t_cam_obj"]).max() < 5e-3
+    assert np.abs(out["code"] - d["code"]).max() < 8e-3
+    assert abs(float(out["loss"]) - float(d["loss"])) < 0.02 * abs(float(d["loss"]))
